@@ -1,0 +1,42 @@
+"""Build libfsar_sm100.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "csrc", "fsar.cu")
+OUT = os.path.join(HERE, "libfsar_sm100.so")
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("fsar.cu", "ptx.cuh", "gemm_tcgen05.cuh", "vit_kernels.cuh",
+                                                "head_kernels.cuh")] + [os.path.join(HERE, "..", "include", "fsar.h")]
+
+
+def nvcc_cmd(extra=()):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+            "-Xcompiler", "-fPIC", "-cudart", "static", *extra, "-o", OUT, SRC]
+
+
+def up_to_date():
+    if not os.path.exists(OUT):
+        return False
+    t = os.path.getmtime(OUT)
+    return all(os.path.getmtime(d) <= t for d in DEPS)
+
+
+def build(force=False, verbose=False, bf16=False):
+    if not force and up_to_date():
+        return OUT
+    extra = ["-Xptxas", "-v"] if verbose else []
+    if bf16:
+        extra.append("-DFSAR_BF16")
+    r = subprocess.run(nvcc_cmd(extra), capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building %s" % OUT)
+    if verbose:
+        sys.stderr.write(r.stderr)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,943 @@
+// libfsar_sm100.so — host side of the C ABI declared in include/fsar.h.
+//
+// Owns: the packed weights (fp32 masters + 16-bit tensor-core operands), the activation workspace, the TMA
+// tensor maps, the kernel launch sequence of the CLIP ViT frame encoder, the temporal prototype modulator
+// and the cosine/OTAM head. There is no CPU path: every entry point needs an sm_100 device.
+//
+// Reference semantics replaced here (all in /root/reference/models/base/few_shot.py):
+//   VisionTransformer.forward 671-688, ResidualAttentionBlock 633-640, Transformer_v1.forward 990-999,
+//   CNN_OTAM_CLIPFSAR.forward eval branch 2932-2990.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/fsar.h"
+#include "gemm_tcgen05.cuh"
+#include "head_kernels.cuh"
+#include "vit_kernels.cuh"
+
+using namespace fsar;
+
+#ifdef FSAR_BF16
+typedef __nv_bfloat16 T16;
+static const int kOperandDtype = 1;
+#else
+typedef __half T16;
+static const int kOperandDtype = 0;
+#endif
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Weight {
+    std::string name;
+    int64_t numel = 0;
+    float* d32 = nullptr;  // fp32 master (device); may point into a shared allocation (owns32 == false)
+    T16* d16 = nullptr;    // 16-bit [rows, kp] operand for the tensor-core GEMMs, or nullptr
+    int rows = 0, cols = 0, kp = 0;
+    bool owns32 = true;
+    bool set = false;
+    bool required = true;
+};
+
+struct ProfRec {
+    int cls;
+    cudaEvent_t a, b;
+    double flops, bytes;
+};
+
+struct HostSlot {
+    float* frames_dev = nullptr;   // [max_videos * max_tokens, 3, S, S]: support first, then target
+    float* labels_dev = nullptr;   // [2 * max_videos]: support_labels | real_support_labels
+    float* logits_dev = nullptr;   // [max_videos * max_videos]
+    float* clogits_dev = nullptr;  // [max_videos * max_classes]
+    float* logits_pin = nullptr;   // pinned host mirrors
+    float* clogits_pin = nullptr;
+    cudaEvent_t copied = nullptr, done = nullptr;
+    int n_support = 0, n_target = 0, way = 0, busy = 0;
+};
+
+}  // namespace
+
+struct fsar_handle {
+    fsar_config cfg;
+    std::string err;
+    int tokens = 0, grid = 0, patch_k = 0, patch_kp = 0, sms = 148;
+    std::vector<Weight> w;
+    std::unordered_map<std::string, int> widx;
+    std::vector<std::string> missing_cache;
+    int n_text_train = 0, n_text_test = 0;
+    // fused modulator QKV weights: one [3 * inner, E] allocation per layer
+    std::vector<float*> mod_qkv;
+    // ---- ViT workspace (capacity cfg.max_frames)
+    T16 *patches16 = nullptr, *ln16 = nullptr, *qkv16 = nullptr, *att16 = nullptr, *h16 = nullptr;
+    float* x32 = nullptr;
+    // ---- head workspace
+    float *feats = nullptr;  // [max_videos * max_tokens, E] support rows then target rows
+    float *seq = nullptr, *mod_ln = nullptr, *mod_qkvbuf = nullptr, *mod_att = nullptr, *mod_y = nullptr,
+          *mod_h = nullptr, *mod_out = nullptr, *mod_tmp = nullptr;
+    float *protos = nullptr, *dists = nullptr, *cum = nullptr;
+    int *cls = nullptr, *counts = nullptr;
+    // last episode geometry (for fsar_peek)
+    int last_S = 0, last_Q = 0, last_T = 0, last_way = 0, last_rows = 0;
+    // ---- TMA
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    EncodeFn encode = nullptr;
+    std::map<std::tuple<const void*, int, int, int>, CUtensorMap> tmaps;
+    // ---- host-buffer path
+    HostSlot slot[2];
+    cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+    // ---- instrumentation
+    int64_t launches = 0;
+    bool profiling = false;
+    std::vector<ProfRec> prof;
+};
+
+namespace {
+
+int fail(fsar_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU_OK(h, expr)                                                                                    \
+    do {                                                                                                  \
+        cudaError_t e__ = (expr);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return fail(h, FSAR_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                                        \
+    } while (0)
+
+#define RET_IF(expr)          \
+    do {                      \
+        int r__ = (expr);     \
+        if (r__ != 0) return r__; \
+    } while (0)
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// ---------------------------------------------------------------- profiling helpers
+struct Scope {
+    fsar_handle* h;
+    cudaStream_t st;
+    int cls;
+    double flops, bytes;
+    cudaEvent_t a = nullptr, b = nullptr;
+    Scope(fsar_handle* h_, cudaStream_t st_, int cls_, double flops_, double bytes_)
+        : h(h_), st(st_), cls(cls_), flops(flops_), bytes(bytes_) {
+        if (h->profiling) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, st);
+        }
+    }
+    ~Scope() {
+        h->launches += 1;
+        if (h->profiling) {
+            cudaEventRecord(b, st);
+            h->prof.push_back(ProfRec{cls, a, b, flops, bytes});
+        }
+    }
+};
+
+int check_launch(fsar_handle* h, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, FSAR_E_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
+// ---------------------------------------------------------------- TMA tensor maps
+// Row-major 16-bit matrix [rows, cols] (cols contiguous), box = [box_rows, 64 cols], 128-byte swizzle.
+int get_tmap(fsar_handle* h, const void* ptr, int rows, int cols, int box_rows, CUtensorMap* out) {
+    auto key = std::make_tuple(ptr, rows, cols, box_rows);
+    auto it = h->tmaps.find(key);
+    if (it != h->tmaps.end()) {
+        *out = it->second;
+        return 0;
+    }
+    if ((cols % 8) != 0) return fail(h, FSAR_E_INVALID, "TMA needs a 16-byte row pitch (cols %% 8 == 0), got %d", cols);
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMapDataType dt = kOperandDtype ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUresult r = h->encode(&m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, FSAR_E_CUDA, "cuTensorMapEncodeTiled failed with %d (rows %d cols %d)", (int)r, rows, cols);
+    if (h->tmaps.size() > 4096) h->tmaps.clear();
+    h->tmaps[key] = m;
+    *out = m;
+    return 0;
+}
+
+// ---------------------------------------------------------------- GEMM dispatch
+template <int BN, int EPI>
+int launch_gemm_inst(fsar_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                     cudaStream_t st) {
+    typedef GemmCfg<BN> Cfg;
+    auto kern = gemm_tn_tcgen05_kernel<BN, EPI, T16>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CU_OK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_done = true;
+    }
+    const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (p.N + BN - 1) / BN;
+    const int tiles = m_tiles * n_tiles;
+    const int grid = tiles < h->sms ? tiles : h->sms;
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+    return check_launch(h, "gemm_tn_tcgen05_kernel");
+}
+
+template <int BN>
+int launch_gemm_bn(fsar_handle* h, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                   cudaStream_t st) {
+    switch (epi) {
+        case EPI_STORE16: return launch_gemm_inst<BN, EPI_STORE16>(h, ta, tb, p, st);
+        case EPI_QGELU16: return launch_gemm_inst<BN, EPI_QGELU16>(h, ta, tb, p, st);
+        case EPI_RESID32: return launch_gemm_inst<BN, EPI_RESID32>(h, ta, tb, p, st);
+        case EPI_PATCH32: return launch_gemm_inst<BN, EPI_PATCH32>(h, ta, tb, p, st);
+        case EPI_STORE32: return launch_gemm_inst<BN, EPI_STORE32>(h, ta, tb, p, st);
+    }
+    return fail(h, FSAR_E_INVALID, "unknown GEMM epilogue %d", epi);
+}
+
+// C[M,N] = A16[M,K] W16[N,K]^T, K = row pitch of both operands.
+int gemm(fsar_handle* h, int cls, const T16* a, const T16* w, int M, int N, int K, int epi, GemmParams p,
+         cudaStream_t st) {
+    if (M <= 0 || N <= 0 || K <= 0 || (N % 8) != 0 || (K % 8) != 0)
+        return fail(h, FSAR_E_INVALID, "gemm: unsupported shape M=%d N=%d K=%d (need N %% 8 == 0, K %% 8 == 0)", M, N, K);
+    p.M = M; p.N = N; p.K = K;
+    const int bn = (N >= 256) ? 256 : ((N >= 128) ? 128 : 64);
+    CUtensorMap ta, tb;
+    RET_IF(get_tmap(h, a, M, K, GEMM_BM, &ta));
+    RET_IF(get_tmap(h, w, N, K, bn, &tb));
+    Scope s(h, st, cls, 2.0 * M * N * K, 0.0);
+    if (bn == 256) return launch_gemm_bn<256>(h, epi, ta, tb, p, st);
+    if (bn == 128) return launch_gemm_bn<128>(h, epi, ta, tb, p, st);
+    return launch_gemm_bn<64>(h, epi, ta, tb, p, st);
+}
+
+// ---------------------------------------------------------------- small launch wrappers
+__global__ void f32_to_16_kernel(const float* __restrict__ src, T16* __restrict__ dst, long long n) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        const float4 v = *reinterpret_cast<const float4*>(src + i);
+        uint2 w;
+        w.x = pack2<T16>(v.x, v.y);
+        w.y = pack2<T16>(v.z, v.w);
+        *reinterpret_cast<uint2*>(dst + i) = w;
+    } else {
+        for (; i < n; ++i) dst[i] = T16(src[i]);
+    }
+}
+
+// weight [rows, cols] fp32 -> [rows, kp] 16-bit, zero padded columns
+__global__ void pack_weight_kernel(const float* __restrict__ src, T16* __restrict__ dst, int rows, int cols, int kp) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)rows * kp) return;
+    const int r = int(i / kp), c = int(i - (long long)r * kp);
+    dst[i] = (c < cols) ? T16(src[(size_t)r * cols + c]) : T16(0.f);
+}
+
+int layernorm(fsar_handle* h, const float* x, void* out, const float* g, const float* b, int rows, int D, bool out16,
+              bool cls_fill, int tokens, const float* cls_emb, const float* pos0, cudaStream_t st, int cls) {
+    if ((D % 128) != 0 || D > 1024) return fail(h, FSAR_E_INVALID, "layernorm: dim %d must be a multiple of 128 and <= 1024", D);
+    const int wpb = 8;
+    const int grid = (rows + wpb - 1) / wpb;
+    Scope s(h, st, cls, 0.0, (double)rows * D * (4.0 + (out16 ? 2.0 : 4.0)));
+    if (cls_fill)
+        layernorm_kernel<T16, false, true><<<grid, 256, 0, st>>>(x, out, g, b, rows, D, 1e-5f, tokens, cls_emb, pos0);
+    else if (out16)
+        layernorm_kernel<T16, true, false><<<grid, 256, 0, st>>>(x, out, g, b, rows, D, 1e-5f, tokens, nullptr, nullptr);
+    else
+        layernorm_kernel<T16, false, false><<<grid, 256, 0, st>>>(x, out, g, b, rows, D, 1e-5f, tokens, nullptr, nullptr);
+    return check_launch(h, "layernorm_kernel");
+}
+
+int attention(fsar_handle* h, const T16* qkv, int n_frames, int L, int heads, T16* out, cudaStream_t st) {
+    const int D = heads * ATT_HD;
+    const dim3 grid((L + ATT_QROWS - 1) / ATT_QROWS, heads, n_frames);
+    const float scale_log2e = 0.125f * 1.4426950408889634f;  // head_dim ** -0.5 * log2(e)
+    Scope s(h, st, FSAR_K_ATTENTION, 4.0 * n_frames * heads * (double)L * L * ATT_HD,
+            (double)n_frames * L * D * 2.0 * 4.0);
+    if (L <= 208) {
+        static bool done = false;
+        if (!done) {
+            CU_OK(h, cudaFuncSetAttribute(attention_mma_kernel<T16, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          att_smem_bytes<13>()));
+            done = true;
+        }
+        attention_mma_kernel<T16, 13><<<grid, 128, att_smem_bytes<13>(), st>>>(qkv, out, L, D, scale_log2e);
+    } else if (L <= 272) {
+        static bool done = false;
+        if (!done) {
+            CU_OK(h, cudaFuncSetAttribute(attention_mma_kernel<T16, 17>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          att_smem_bytes<17>()));
+            done = true;
+        }
+        attention_mma_kernel<T16, 17><<<grid, 128, att_smem_bytes<17>(), st>>>(qkv, out, L, D, scale_log2e);
+    } else {
+        return fail(h, FSAR_E_INVALID, "attention: %d tokens per frame exceeds the supported 272", L);
+    }
+    return check_launch(h, "attention_mma_kernel");
+}
+
+template <int ACT>
+int linear_f32(fsar_handle* h, const float* A, const float* W, const float* bias, const float* residual, float* C, int R,
+               int N, int K, cudaStream_t st) {
+    const dim3 grid((N + LIN_BN - 1) / LIN_BN, (R + LIN_BM - 1) / LIN_BM);
+    Scope s(h, st, FSAR_K_MODULATOR, 2.0 * R * N * K, 4.0 * ((double)N * K + (double)R * K + (double)R * N));
+    linear_f32_kernel<ACT><<<grid, 256, 0, st>>>(A, W, bias, residual, C, R, N, K);
+    return check_launch(h, "linear_f32_kernel");
+}
+
+// ---------------------------------------------------------------- weights
+Weight* find_w(fsar_handle* h, const std::string& name) {
+    auto it = h->widx.find(name);
+    return it == h->widx.end() ? nullptr : &h->w[it->second];
+}
+const float* W32(fsar_handle* h, const std::string& name) { return find_w(h, name)->d32; }
+const T16* W16(fsar_handle* h, const std::string& name) { return find_w(h, name)->d16; }
+
+void add_w(fsar_handle* h, const std::string& name, int64_t numel, int rows = 0, int cols = 0, int kp = 0,
+           bool required = true) {
+    Weight w;
+    w.name = name; w.numel = numel; w.rows = rows; w.cols = cols; w.kp = kp; w.required = required;
+    h->widx[name] = (int)h->w.size();
+    h->w.push_back(w);
+}
+
+int alloc_weights(fsar_handle* h) {
+    const fsar_config& c = h->cfg;
+    const int D = c.width, E = c.embed_dim, P = c.patch_size;
+    const int inner = c.mod_heads * c.mod_dim_head, F = c.mod_mlp_dim;
+    add_w(h, "backbone.conv1.weight", (int64_t)D * 3 * P * P, D, 3 * P * P, h->patch_kp);
+    add_w(h, "backbone.class_embedding", D);
+    add_w(h, "backbone.positional_embedding", (int64_t)h->tokens * D);
+    add_w(h, "backbone.ln_pre.weight", D);
+    add_w(h, "backbone.ln_pre.bias", D);
+    add_w(h, "backbone.ln_post.weight", D);
+    add_w(h, "backbone.ln_post.bias", D);
+    add_w(h, "backbone.proj", (int64_t)D * E);
+    for (int i = 0; i < c.layers; ++i) {
+        const std::string p = "backbone.transformer.resblocks." + std::to_string(i) + ".";
+        add_w(h, p + "attn.in_proj_weight", (int64_t)3 * D * D, 3 * D, D, D);
+        add_w(h, p + "attn.in_proj_bias", 3 * D);
+        add_w(h, p + "attn.out_proj.weight", (int64_t)D * D, D, D, D);
+        add_w(h, p + "attn.out_proj.bias", D);
+        add_w(h, p + "ln_1.weight", D);
+        add_w(h, p + "ln_1.bias", D);
+        add_w(h, p + "ln_2.weight", D);
+        add_w(h, p + "ln_2.bias", D);
+        add_w(h, p + "mlp.c_fc.weight", (int64_t)4 * D * D, 4 * D, D, D);
+        add_w(h, p + "mlp.c_fc.bias", 4 * D);
+        add_w(h, p + "mlp.c_proj.weight", (int64_t)4 * D * D, D, 4 * D, 4 * D);
+        add_w(h, p + "mlp.c_proj.bias", D);
+    }
+    add_w(h, "scale", 1);
+    for (int l = 0; l < c.mod_depth; ++l) {
+        const std::string p = "context2.layers." + std::to_string(l) + ".";
+        add_w(h, p + "0.norm.weight", E);
+        add_w(h, p + "0.norm.bias", E);
+        add_w(h, p + "0.fn.to_q.weight", (int64_t)inner * E);
+        add_w(h, p + "0.fn.to_k.weight", (int64_t)inner * E);
+        add_w(h, p + "0.fn.to_v.weight", (int64_t)inner * E);
+        add_w(h, p + "0.fn.to_out.0.weight", (int64_t)E * inner);
+        add_w(h, p + "0.fn.to_out.0.bias", E);
+        add_w(h, p + "1.net.0.weight", (int64_t)F * E);
+        add_w(h, p + "1.net.0.bias", F);
+        add_w(h, p + "1.net.3.weight", (int64_t)E * F);
+        add_w(h, p + "1.net.3.bias", E);
+    }
+    add_w(h, "text_features_train", (int64_t)c.max_classes * E, 0, 0, 0, false);
+    add_w(h, "text_features_test", (int64_t)c.max_classes * E, 0, 0, 0, false);
+
+    h->mod_qkv.assign(c.mod_depth, nullptr);
+    for (int l = 0; l < c.mod_depth; ++l)
+        CU_OK(h, cudaMalloc(&h->mod_qkv[l], sizeof(float) * 3 * (size_t)inner * E));
+    for (auto& w : h->w) {
+        // the three modulator projections of a layer live in one [3 * inner, E] buffer (one fused launch)
+        size_t pos;
+        int which = -1;
+        if ((pos = w.name.find(".0.fn.to_q.weight")) != std::string::npos) which = 0;
+        else if ((pos = w.name.find(".0.fn.to_k.weight")) != std::string::npos) which = 1;
+        else if ((pos = w.name.find(".0.fn.to_v.weight")) != std::string::npos) which = 2;
+        if (which >= 0) {
+            const int l = atoi(w.name.c_str() + strlen("context2.layers."));
+            w.d32 = h->mod_qkv[l] + (size_t)which * inner * E;
+            w.owns32 = false;
+        } else {
+            CU_OK(h, cudaMalloc(&w.d32, sizeof(float) * (size_t)w.numel));
+        }
+        if (w.rows > 0) CU_OK(h, cudaMalloc(&w.d16, sizeof(T16) * (size_t)w.rows * w.kp));
+    }
+    return 0;
+}
+
+template <typename T>
+int dalloc(fsar_handle* h, T** p, size_t n) {
+    CU_OK(h, cudaMalloc(p, sizeof(T) * (n ? n : 1)));
+    return 0;
+}
+
+int alloc_workspace(fsar_handle* h) {
+    const fsar_config& c = h->cfg;
+    const size_t D = c.width, E = c.embed_dim;
+    const size_t M = (size_t)c.max_frames * h->tokens;
+    const size_t Mp = (size_t)c.max_frames * h->grid * h->grid;
+    RET_IF(dalloc(h, &h->patches16, Mp * h->patch_kp));
+    CU_OK(h, cudaMemset(h->patches16, 0, sizeof(T16) * Mp * h->patch_kp));
+    RET_IF(dalloc(h, &h->x32, M * D));
+    RET_IF(dalloc(h, &h->ln16, M * D));
+    RET_IF(dalloc(h, &h->qkv16, M * 3 * D));
+    RET_IF(dalloc(h, &h->att16, M * D));
+    RET_IF(dalloc(h, &h->h16, M * 4 * D));
+    const size_t V = c.max_videos, T = c.max_tokens;
+    const size_t rows = V * (T + 1);
+    const size_t inner = (size_t)c.mod_heads * c.mod_dim_head;
+    RET_IF(dalloc(h, &h->feats, V * T * E));
+    RET_IF(dalloc(h, &h->seq, rows * E));
+    RET_IF(dalloc(h, &h->mod_ln, rows * E));
+    RET_IF(dalloc(h, &h->mod_qkvbuf, rows * 3 * inner));
+    RET_IF(dalloc(h, &h->mod_att, rows * inner));
+    RET_IF(dalloc(h, &h->mod_y, rows * E));
+    RET_IF(dalloc(h, &h->mod_h, rows * (size_t)c.mod_mlp_dim));
+    RET_IF(dalloc(h, &h->mod_out, rows * E));
+    RET_IF(dalloc(h, &h->mod_tmp, rows * E));
+    RET_IF(dalloc(h, &h->protos, V * T * E));
+    RET_IF(dalloc(h, &h->dists, V * V * T * T));
+    RET_IF(dalloc(h, &h->cum, V * V));
+    RET_IF(dalloc(h, &h->cls, V));
+    RET_IF(dalloc(h, &h->counts, V));
+    return 0;
+}
+
+bool ready(fsar_handle* h, bool need_text) {
+    for (auto& w : h->w)
+        if (!w.set && (w.required || need_text)) return false;
+    return true;
+}
+
+// ---------------------------------------------------------------- the ViT frame encoder
+// Encodes `n` frames whose patches are already gathered into h->patches16 rows [0, n * G * G).
+int vit_encode_gathered(fsar_handle* h, int n, float* feats_out, cudaStream_t st) {
+    const fsar_config& c = h->cfg;
+    const int D = c.width, L = h->tokens, G2 = h->grid * h->grid;
+    const int M = n * L;
+    {   // conv1 as a GEMM; the epilogue adds the positional embedding and scatters to token rows 1..G*G
+        GemmParams p{};
+        p.bias = nullptr; p.out = h->x32; p.ldo = D;
+        p.pos = W32(h, "backbone.positional_embedding"); p.patches_per_frame = G2;
+        RET_IF(gemm(h, FSAR_K_GEMM_PATCH, h->patches16, W16(h, "backbone.conv1.weight"), n * G2, D, h->patch_kp,
+                    EPI_PATCH32, p, st));
+    }
+    // ln_pre in place; CLS rows take class_embedding + positional_embedding[0] as their input
+    RET_IF(layernorm(h, h->x32, h->x32, W32(h, "backbone.ln_pre.weight"), W32(h, "backbone.ln_pre.bias"), M, D, false,
+                     true, L, W32(h, "backbone.class_embedding"), W32(h, "backbone.positional_embedding"), st,
+                     FSAR_K_LAYERNORM));
+    for (int i = 0; i < c.layers; ++i) {
+        const std::string pre = "backbone.transformer.resblocks." + std::to_string(i) + ".";
+        RET_IF(layernorm(h, h->x32, h->ln16, W32(h, pre + "ln_1.weight"), W32(h, pre + "ln_1.bias"), M, D, true, false, L,
+                         nullptr, nullptr, st, FSAR_K_LAYERNORM));
+        GemmParams p{};
+        p.bias = W32(h, pre + "attn.in_proj_bias"); p.out = h->qkv16; p.ldo = 3 * D;
+        RET_IF(gemm(h, FSAR_K_GEMM_QKV, h->ln16, W16(h, pre + "attn.in_proj_weight"), M, 3 * D, D, EPI_STORE16, p, st));
+        RET_IF(attention(h, h->qkv16, n, L, c.heads, h->att16, st));
+        p.bias = W32(h, pre + "attn.out_proj.bias"); p.out = h->x32; p.ldo = D;
+        RET_IF(gemm(h, FSAR_K_GEMM_OUT, h->att16, W16(h, pre + "attn.out_proj.weight"), M, D, D, EPI_RESID32, p, st));
+        RET_IF(layernorm(h, h->x32, h->ln16, W32(h, pre + "ln_2.weight"), W32(h, pre + "ln_2.bias"), M, D, true, false, L,
+                         nullptr, nullptr, st, FSAR_K_LAYERNORM));
+        p.bias = W32(h, pre + "mlp.c_fc.bias"); p.out = h->h16; p.ldo = 4 * D;
+        RET_IF(gemm(h, FSAR_K_GEMM_FC1, h->ln16, W16(h, pre + "mlp.c_fc.weight"), M, 4 * D, D, EPI_QGELU16, p, st));
+        p.bias = W32(h, pre + "mlp.c_proj.bias"); p.out = h->x32; p.ldo = D;
+        RET_IF(gemm(h, FSAR_K_GEMM_FC2, h->h16, W16(h, pre + "mlp.c_proj.weight"), M, D, 4 * D, EPI_RESID32, p, st));
+    }
+    {
+        const int grid = (n + FINAL_FPC - 1) / FINAL_FPC;
+        Scope s(h, st, FSAR_K_FINAL_PROJ, 2.0 * n * D * c.embed_dim, 4.0 * ((double)D * c.embed_dim + (double)n * D));
+        final_proj_kernel<<<grid, 256, sizeof(float) * FINAL_FPC * D, st>>>(
+            h->x32, W32(h, "backbone.ln_post.weight"), W32(h, "backbone.ln_post.bias"), W32(h, "backbone.proj"),
+            feats_out, n, L, D, c.embed_dim, 1e-5f);
+        RET_IF(check_launch(h, "final_proj_kernel"));
+    }
+    return 0;
+}
+
+int patch_gather(fsar_handle* h, const float* frames, int n, int row_frame_offset, cudaStream_t st) {
+    const fsar_config& c = h->cfg;
+    const int S = c.image_size, P = c.patch_size, G = h->grid;
+    const long long total = (long long)n * 3 * S * G;
+    const int grid = (int)((total + 255) / 256);
+    Scope s(h, st, FSAR_K_PATCH_GATHER, 0.0, (double)n * 3 * S * S * 6.0);
+    patch_gather_kernel<T16><<<grid, 256, 0, st>>>(frames, h->patches16 + (size_t)row_frame_offset * G * G * h->patch_kp,
+                                                   n, S, P, h->patch_kp);
+    return check_launch(h, "patch_gather_kernel");
+}
+
+// Encode frames from up to two device buffers (support frames then target frames) into feats rows
+// [0, n0 + n1), in passes of at most cfg.max_frames frames.
+int vit_encode_segments(fsar_handle* h, const float* f0, int n0, const float* f1, int n1, float* feats, cudaStream_t st) {
+    const fsar_config& c = h->cfg;
+    const size_t frame_elems = (size_t)3 * c.image_size * c.image_size;
+    const int total = n0 + n1;
+    int done = 0;
+    while (done < total) {
+        const int n = (total - done < c.max_frames) ? total - done : c.max_frames;
+        // pieces of this pass: global frame range [done, done + n)
+        int filled = 0;
+        while (filled < n) {
+            const int g = done + filled;
+            const float* src;
+            int avail;
+            if (g < n0) { src = f0 + (size_t)g * frame_elems; avail = n0 - g; }
+            else { src = f1 + (size_t)(g - n0) * frame_elems; avail = total - g; }
+            const int take = (avail < n - filled) ? avail : n - filled;
+            RET_IF(patch_gather(h, src, take, filled, st));
+            filled += take;
+        }
+        RET_IF(vit_encode_gathered(h, n, feats + (size_t)done * c.embed_dim, st));
+        done += n;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------- temporal prototype modulator
+// x [rows, E]: n_q sequences of T tokens followed by n_s sequences of T + 1 tokens -> out [rows, E]
+int modulate_rows(fsar_handle* h, const float* x, int n_q, int n_s, int T, float* out, cudaStream_t st) {
+    const fsar_config& c = h->cfg;
+    const int E = c.embed_dim, inner = c.mod_heads * c.mod_dim_head, F = c.mod_mlp_dim;
+    const int rows = n_q * T + n_s * (T + 1);
+    if (T + 1 > MOD_MAX_TOK) return fail(h, FSAR_E_INVALID, "modulator: %d tokens per sequence exceeds %d", T + 1, MOD_MAX_TOK);
+    const float* cur = x;
+    for (int l = 0; l < c.mod_depth; ++l) {
+        const std::string p = "context2.layers." + std::to_string(l) + ".";
+        // depth > 1: intermediate layers ping-pong between mod_tmp and seq (seq is dead once layer 0 consumed it)
+        float* dst = (l == c.mod_depth - 1) ? out : ((l & 1) ? h->seq : h->mod_tmp);
+        RET_IF(layernorm(h, cur, h->mod_ln, W32(h, p + "0.norm.weight"), W32(h, p + "0.norm.bias"), rows, E, false, false,
+                         1, nullptr, nullptr, st, FSAR_K_MODULATOR));
+        RET_IF(linear_f32<LIN_NONE>(h, h->mod_ln, h->mod_qkv[l], nullptr, nullptr, h->mod_qkvbuf, rows, 3 * inner, E, st));
+        {
+            const int nmax = T + 1, dh = c.mod_dim_head;
+            const size_t smem = sizeof(float) * ((size_t)3 * nmax * dh + (size_t)nmax * (nmax + 1));
+            Scope s(h, st, FSAR_K_MODULATOR, 4.0 * rows * nmax * inner, 4.0 * 4.0 * rows * inner);
+            modulator_attention_kernel<<<dim3(n_q + n_s, c.mod_heads), 128, smem, st>>>(
+                h->mod_qkvbuf, h->mod_qkvbuf + inner, h->mod_qkvbuf + 2 * inner, h->mod_att, n_q, T, 3 * inner, inner, dh,
+                1.0f / sqrtf((float)dh));
+            RET_IF(check_launch(h, "modulator_attention_kernel"));
+        }
+        RET_IF(linear_f32<LIN_NONE>(h, h->mod_att, W32(h, p + "0.fn.to_out.0.weight"), W32(h, p + "0.fn.to_out.0.bias"), cur,
+                                    h->mod_y, rows, E, inner, st));
+        RET_IF(linear_f32<LIN_GELU>(h, h->mod_y, W32(h, p + "1.net.0.weight"), W32(h, p + "1.net.0.bias"), nullptr, h->mod_h,
+                                    rows, F, E, st));
+        RET_IF(linear_f32<LIN_NONE>(h, h->mod_h, W32(h, p + "1.net.3.weight"), W32(h, p + "1.net.3.bias"), h->mod_y, dst,
+                                    rows, E, F, st));
+        cur = dst;
+    }
+    return 0;
+}
+
+int otam_logits(fsar_handle* h, const float* q, const float* protos, int Q, int way, int T, int single_direct,
+                float* logits, float* dists, float* cum, cudaStream_t st) {
+    if (T > OTAM_MAX_T || T < 1) return fail(h, FSAR_E_INVALID, "otam: T=%d outside [1, %d]", T, OTAM_MAX_T);
+    Scope s(h, st, FSAR_K_COS_OTAM, 2.0 * Q * way * T * T * h->cfg.embed_dim,
+            4.0 * ((double)(Q + way) * T * h->cfg.embed_dim + (double)Q * way));
+    cos_otam_kernel<<<dim3(Q, way), 256, 0, st>>>(q, protos, T, h->cfg.embed_dim, way, h->cfg.otam_lambda, single_direct,
+                                                  logits, dists, cum);
+    return check_launch(h, "cos_otam_kernel");
+}
+
+// Everything after the frame encoder: h->feats (support rows then target rows) -> logits, class_logits.
+int head_forward(fsar_handle* h, const float* support_labels, const float* real_support_labels, int S, int Q, int T,
+                 int way, int merge_before, int single_direct, float* logits, float* class_logits, cudaStream_t st) {
+    const fsar_config& c = h->cfg;
+    const int E = c.embed_dim;
+    const float* sup = h->feats;
+    const float* tgt = h->feats + (size_t)S * T * E;
+    {
+        Scope s(h, st, FSAR_K_HEAD_MISC, 0.0, 8.0 * S);
+        class_index_kernel<<<1, 128, 0, st>>>(support_labels, S, h->cls, h->counts, way);
+        RET_IF(check_launch(h, "class_index_kernel"));
+    }
+    if (class_logits != nullptr) {
+        if (!find_w(h, "text_features_train")->set) return fail(h, FSAR_E_STATE, "text_features_train has not been set");
+        Scope s(h, st, FSAR_K_HEAD_MISC, 2.0 * (S + Q) * h->n_text_train * E,
+                4.0 * ((double)(S + Q) * T * E + (double)h->n_text_train * E));
+        class_text_logits_kernel<<<S + Q, 256, sizeof(float) * E, st>>>(sup, S, tgt, Q, T, E, W32(h, "text_features_train"),
+                                                                        h->n_text_train, W32(h, "scale"), class_logits);
+        RET_IF(check_launch(h, "class_text_logits_kernel"));
+    }
+    const int n_sup_seq = merge_before ? way : S;
+    const int rows = Q * T + n_sup_seq * (T + 1);
+    {
+        Scope s(h, st, FSAR_K_HEAD_MISC, 0.0, 8.0 * rows * E);
+        build_sequences_kernel<<<rows, 128, 0, st>>>(sup, tgt, W32(h, "text_features_test"), real_support_labels, h->cls,
+                                                     h->counts, S, Q, T, E, way, merge_before, h->seq);
+        RET_IF(check_launch(h, "build_sequences_kernel"));
+    }
+    // depth > 1 uses h->seq as a ping-pong buffer, so the first layer must not read it after layer 2 wrote it:
+    // layer l reads `cur` and writes dst != cur, and h->seq is only overwritten at l = 1 (after l = 0 consumed it).
+    RET_IF(modulate_rows(h, h->seq, Q, n_sup_seq, T, h->mod_out, st));
+    {
+        Scope s(h, st, FSAR_K_HEAD_MISC, 0.0, 8.0 * way * T * E);
+        prototype_kernel<<<way * T, 128, 0, st>>>(h->mod_out, Q * T, n_sup_seq, T, E, h->cls, h->counts, merge_before,
+                                                  h->protos);
+        RET_IF(check_launch(h, "prototype_kernel"));
+    }
+    RET_IF(otam_logits(h, h->mod_out, h->protos, Q, way, T, single_direct, logits, h->dists, h->cum, st));
+    h->last_S = S; h->last_Q = Q; h->last_T = T; h->last_way = way; h->last_rows = rows;
+    return 0;
+}
+
+int check_episode(fsar_handle* h, const fsar_episode* ep) {
+    const fsar_config& c = h->cfg;
+    if (ep == nullptr) return fail(h, FSAR_E_INVALID, "episode is NULL");
+    if (ep->n_support < 1 || ep->n_target < 1 || ep->n_frames < 1 || ep->way < 1 || ep->way > ep->n_support)
+        return fail(h, FSAR_E_INVALID, "episode: bad geometry S=%d Q=%d T=%d way=%d", ep->n_support, ep->n_target,
+                    ep->n_frames, ep->way);
+    if (ep->n_support + ep->n_target > c.max_videos || ep->n_frames > c.max_tokens)
+        return fail(h, FSAR_E_STATE, "episode exceeds capacity: %d videos (max %d), %d frames (max %d)",
+                    ep->n_support + ep->n_target, c.max_videos, ep->n_frames, c.max_tokens);
+    if (!ready(h, true)) return fail(h, FSAR_E_STATE, "%d weights have not been set", fsar_missing_weights(h));
+    return 0;
+}
+
+int episode_forward_dev(fsar_handle* h, const fsar_episode* ep, float* logits, float* class_logits, cudaStream_t st) {
+    const int T = ep->n_frames;
+    RET_IF(vit_encode_segments(h, ep->support_frames, ep->n_support * T, ep->target_frames, ep->n_target * T, h->feats, st));
+    return head_forward(h, ep->support_labels, ep->real_support_labels, ep->n_support, ep->n_target, T, ep->way,
+                        ep->merge_before, ep->single_direct, logits, class_logits, st);
+}
+
+int ensure_host_path(fsar_handle* h) {
+    if (h->copy_stream != nullptr) return 0;
+    const fsar_config& c = h->cfg;
+    const size_t frame_elems = (size_t)3 * c.image_size * c.image_size;
+    const size_t V = c.max_videos;
+    CU_OK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CU_OK(h, cudaStreamCreateWithFlags(&h->compute_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        HostSlot& s = h->slot[i];
+        RET_IF(dalloc(h, &s.frames_dev, V * c.max_tokens * frame_elems));
+        RET_IF(dalloc(h, &s.labels_dev, 2 * V));
+        RET_IF(dalloc(h, &s.logits_dev, V * V));
+        RET_IF(dalloc(h, &s.clogits_dev, V * (size_t)c.max_classes));
+        CU_OK(h, cudaMallocHost(&s.logits_pin, sizeof(float) * V * V));
+        CU_OK(h, cudaMallocHost(&s.clogits_pin, sizeof(float) * V * c.max_classes));
+        CU_OK(h, cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+        CU_OK(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int fsar_version(void) { return FSAR_VERSION; }
+
+const char* fsar_class_name(int k) {
+    static const char* names[FSAR_PROF_CLASSES] = {"patch_gather", "gemm_patch", "layernorm", "gemm_qkv", "attention",
+                                                   "gemm_out", "gemm_fc1", "gemm_fc2", "final_proj", "head_misc",
+                                                   "modulator", "cos_otam"};
+    return (k >= 0 && k < FSAR_PROF_CLASSES) ? names[k] : "?";
+}
+
+int fsar_operand_dtype(void) { return kOperandDtype; }
+
+const char* fsar_last_error(const fsar_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int fsar_create(const fsar_config* cfg, fsar_handle** out) {
+    if (cfg == nullptr || out == nullptr) return fail(nullptr, FSAR_E_INVALID, "fsar_create: NULL argument");
+    *out = nullptr;
+    const fsar_config& c = *cfg;
+    if (c.patch_size <= 0 || c.image_size % c.patch_size != 0 || (c.patch_size & 1))
+        return fail(nullptr, FSAR_E_INVALID, "image_size %d must be a multiple of an even patch_size %d", c.image_size, c.patch_size);
+    if (c.width % 128 != 0 || c.width > 1024 || c.heads * 64 != c.width)
+        return fail(nullptr, FSAR_E_INVALID, "width %d must be a multiple of 128, <= 1024 and equal heads * 64 (heads %d)", c.width, c.heads);
+    if (c.embed_dim % 128 != 0 || c.embed_dim > 1024 || c.mod_heads * c.mod_dim_head <= 0 || c.mod_depth < 1 || c.layers < 1)
+        return fail(nullptr, FSAR_E_INVALID, "unsupported head geometry (embed_dim %d, mod heads %d x %d, depth %d)", c.embed_dim, c.mod_heads, c.mod_dim_head, c.mod_depth);
+    if (c.max_frames < 1 || c.max_videos < 2 || c.max_tokens < 1 || c.max_tokens > OTAM_MAX_T || c.max_classes < 1)
+        return fail(nullptr, FSAR_E_INVALID, "bad capacities (max_frames %d, max_videos %d, max_tokens %d <= %d, max_classes %d)", c.max_frames, c.max_videos, c.max_tokens, OTAM_MAX_T, c.max_classes);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= c.device || c.device < 0) {
+        cudaGetLastError();
+        return fail(nullptr, FSAR_E_CUDA, "no CUDA device %d (found %d); libfsar_sm100 has no CPU path", c.device, ndev);
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, c.device) != cudaSuccess || prop.major != 10)
+        return fail(nullptr, FSAR_E_CUDA, "device %d is sm_%d%d; libfsar_sm100 only runs on sm_100 (B200)", c.device, prop.major, prop.minor);
+    fsar_handle* h = new fsar_handle();
+    h->cfg = c;
+    h->sms = prop.multiProcessorCount;
+    h->grid = c.image_size / c.patch_size;
+    h->tokens = h->grid * h->grid + 1;
+    h->patch_k = 3 * c.patch_size * c.patch_size;
+    h->patch_kp = round_up(h->patch_k, GEMM_BK);
+    int rc = 0;
+    do {
+        if (cudaSetDevice(c.device) != cudaSuccess) { rc = fail(nullptr, FSAR_E_CUDA, "cudaSetDevice(%d) failed", c.device); break; }
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr) {
+            rc = fail(nullptr, FSAR_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+            break;
+        }
+        h->encode = reinterpret_cast<fsar_handle::EncodeFn>(fn);
+        if ((rc = alloc_weights(h)) != 0) break;
+        if ((rc = alloc_workspace(h)) != 0) break;
+    } while (0);
+    if (rc != 0) {
+        if (!h->err.empty()) g_create_error = h->err;
+        fsar_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return 0;
+}
+
+void fsar_destroy(fsar_handle* h) {
+    if (h == nullptr) return;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    for (auto& w : h->w) {
+        if (w.owns32 && w.d32) cudaFree(w.d32);
+        if (w.d16) cudaFree(w.d16);
+    }
+    for (float* p : h->mod_qkv) if (p) cudaFree(p);
+    void* bufs[] = {h->patches16, h->ln16, h->qkv16, h->att16, h->h16, h->x32, h->feats, h->seq, h->mod_ln, h->mod_qkvbuf,
+                    h->mod_att, h->mod_y, h->mod_h, h->mod_out, h->mod_tmp, h->protos, h->dists, h->cum, h->cls, h->counts};
+    for (void* p : bufs) if (p) cudaFree(p);
+    for (int i = 0; i < 2; ++i) {
+        HostSlot& s = h->slot[i];
+        if (s.frames_dev) cudaFree(s.frames_dev);
+        if (s.labels_dev) cudaFree(s.labels_dev);
+        if (s.logits_dev) cudaFree(s.logits_dev);
+        if (s.clogits_dev) cudaFree(s.clogits_dev);
+        if (s.logits_pin) cudaFreeHost(s.logits_pin);
+        if (s.clogits_pin) cudaFreeHost(s.clogits_pin);
+        if (s.copied) cudaEventDestroy(s.copied);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
+    for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    delete h;
+}
+
+int fsar_set_weight(fsar_handle* h, const char* name, const float* data, int64_t numel, int on_device) {
+    if (h == nullptr || name == nullptr || data == nullptr) return fail(h, FSAR_E_INVALID, "fsar_set_weight: NULL argument");
+    Weight* w = find_w(h, name);
+    if (w == nullptr) return fail(h, FSAR_E_NAME, "unknown weight '%s'", name);
+    const int E = h->cfg.embed_dim;
+    const bool is_text = !w->required;
+    if (is_text) {
+        if (numel <= 0 || numel % E != 0 || numel > w->numel)
+            return fail(h, FSAR_E_INVALID, "%s: numel %lld must be a multiple of embed_dim %d and <= %lld", name,
+                        (long long)numel, E, (long long)w->numel);
+        if (w->name == "text_features_train") h->n_text_train = (int)(numel / E); else h->n_text_test = (int)(numel / E);
+    } else if (numel != w->numel) {
+        return fail(h, FSAR_E_INVALID, "%s: expected %lld elements, got %lld", name, (long long)w->numel, (long long)numel);
+    }
+    CU_OK(h, cudaSetDevice(h->cfg.device));
+    CU_OK(h, cudaMemcpy(w->d32, data, sizeof(float) * (size_t)numel, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    if (w->d16 != nullptr) {
+        const long long n = (long long)w->rows * w->kp;
+        pack_weight_kernel<<<(int)((n + 255) / 256), 256>>>(w->d32, w->d16, w->rows, w->cols, w->kp);
+        RET_IF(check_launch(h, "pack_weight_kernel"));
+        CU_OK(h, cudaDeviceSynchronize());
+    }
+    w->set = true;
+    return 0;
+}
+
+int fsar_missing_weights(const fsar_handle* h) {
+    if (h == nullptr) return -1;
+    int n = 0;
+    for (auto& w : h->w) n += w.set ? 0 : 1;
+    return n;
+}
+
+const char* fsar_missing_weight(const fsar_handle* h, int i) {
+    if (h == nullptr) return nullptr;
+    for (auto& w : h->w)
+        if (!w.set && i-- == 0) return w.name.c_str();
+    return nullptr;
+}
+
+int fsar_vit_forward(fsar_handle* h, const float* frames_dev, int n_frames, float* feats_dev, void* stream) {
+    if (h == nullptr || frames_dev == nullptr || feats_dev == nullptr || n_frames < 1)
+        return fail(h, FSAR_E_INVALID, "fsar_vit_forward: bad argument");
+    if (!ready(h, false)) return fail(h, FSAR_E_STATE, "%d weights have not been set (first: %s)", fsar_missing_weights(h), fsar_missing_weight(h, 0));
+    return vit_encode_segments(h, frames_dev, n_frames, nullptr, 0, feats_dev, (cudaStream_t)stream);
+}
+
+int fsar_modulate(fsar_handle* h, const float* x_dev, int n_seq, int n_tok, float* out_dev, void* stream) {
+    if (h == nullptr || x_dev == nullptr || out_dev == nullptr || n_seq < 1 || n_tok < 1)
+        return fail(h, FSAR_E_INVALID, "fsar_modulate: bad argument");
+    if (!ready(h, false)) return fail(h, FSAR_E_STATE, "%d weights have not been set", fsar_missing_weights(h));
+    if ((size_t)n_seq * n_tok > (size_t)h->cfg.max_videos * (h->cfg.max_tokens + 1))
+        return fail(h, FSAR_E_STATE, "fsar_modulate: %d x %d rows exceed the workspace", n_seq, n_tok);
+    // all sequences have n_tok tokens: express as n_seq "query" sequences of T = n_tok
+    return modulate_rows(h, x_dev, n_seq, 0, n_tok, out_dev, (cudaStream_t)stream);
+}
+
+int fsar_otam_logits(fsar_handle* h, const float* q_dev, const float* protos_dev, int Q, int way, int T, int single_direct,
+                     float* logits_dev, float* dists_dev, float* cum_dev, void* stream) {
+    if (h == nullptr || q_dev == nullptr || protos_dev == nullptr || logits_dev == nullptr || Q < 1 || way < 1)
+        return fail(h, FSAR_E_INVALID, "fsar_otam_logits: bad argument");
+    return otam_logits(h, q_dev, protos_dev, Q, way, T, single_direct, logits_dev, dists_dev, cum_dev, (cudaStream_t)stream);
+}
+
+int fsar_episode_forward(fsar_handle* h, const fsar_episode* ep, float* logits_dev, float* class_logits_dev, void* stream) {
+    if (h == nullptr || logits_dev == nullptr) return fail(h, FSAR_E_INVALID, "fsar_episode_forward: NULL argument");
+    RET_IF(check_episode(h, ep));
+    return episode_forward_dev(h, ep, logits_dev, class_logits_dev, (cudaStream_t)stream);
+}
+
+int fsar_episode_submit_host(fsar_handle* h, int slot, const fsar_episode* ep) {
+    if (h == nullptr || slot < 0 || slot > 1) return fail(h, FSAR_E_INVALID, "fsar_episode_submit_host: bad argument");
+    RET_IF(check_episode(h, ep));
+    CU_OK(h, cudaSetDevice(h->cfg.device));
+    RET_IF(ensure_host_path(h));
+    HostSlot& s = h->slot[slot];
+    if (s.busy) return fail(h, FSAR_E_STATE, "slot %d still holds an uncollected episode", slot);
+    const fsar_config& c = h->cfg;
+    const size_t frame_elems = (size_t)3 * c.image_size * c.image_size;
+    const int S = ep->n_support, Q = ep->n_target, T = ep->n_frames;
+    // the slot's buffers are free once its previous episode finished (done event of that slot was waited in collect)
+    CU_OK(h, cudaMemcpyAsync(s.frames_dev, ep->support_frames, sizeof(float) * S * T * frame_elems, cudaMemcpyHostToDevice, h->copy_stream));
+    CU_OK(h, cudaMemcpyAsync(s.frames_dev + (size_t)S * T * frame_elems, ep->target_frames, sizeof(float) * Q * T * frame_elems, cudaMemcpyHostToDevice, h->copy_stream));
+    CU_OK(h, cudaMemcpyAsync(s.labels_dev, ep->support_labels, sizeof(float) * S, cudaMemcpyHostToDevice, h->copy_stream));
+    CU_OK(h, cudaMemcpyAsync(s.labels_dev + c.max_videos, ep->real_support_labels, sizeof(float) * S, cudaMemcpyHostToDevice, h->copy_stream));
+    CU_OK(h, cudaEventRecord(s.copied, h->copy_stream));
+    CU_OK(h, cudaStreamWaitEvent(h->compute_stream, s.copied, 0));
+    fsar_episode dev = *ep;
+    dev.support_frames = s.frames_dev;
+    dev.target_frames = s.frames_dev + (size_t)S * T * frame_elems;
+    dev.support_labels = s.labels_dev;
+    dev.real_support_labels = s.labels_dev + c.max_videos;
+    RET_IF(episode_forward_dev(h, &dev, s.logits_dev, s.clogits_dev, h->compute_stream));
+    CU_OK(h, cudaMemcpyAsync(s.logits_pin, s.logits_dev, sizeof(float) * Q * ep->way, cudaMemcpyDeviceToHost, h->compute_stream));
+    CU_OK(h, cudaMemcpyAsync(s.clogits_pin, s.clogits_dev, sizeof(float) * (S + Q) * h->n_text_train, cudaMemcpyDeviceToHost, h->compute_stream));
+    CU_OK(h, cudaEventRecord(s.done, h->compute_stream));
+    s.n_support = S; s.n_target = Q; s.way = ep->way; s.busy = 1;
+    return 0;
+}
+
+int fsar_episode_collect_host(fsar_handle* h, int slot, float* logits_host, float* class_logits_host) {
+    if (h == nullptr || slot < 0 || slot > 1) return fail(h, FSAR_E_INVALID, "fsar_episode_collect_host: bad argument");
+    HostSlot& s = h->slot[slot];
+    if (!s.busy) return fail(h, FSAR_E_STATE, "slot %d holds no submitted episode", slot);
+    CU_OK(h, cudaEventSynchronize(s.done));
+    s.busy = 0;
+    if (logits_host) memcpy(logits_host, s.logits_pin, sizeof(float) * s.n_target * s.way);
+    if (class_logits_host) memcpy(class_logits_host, s.clogits_pin, sizeof(float) * (s.n_support + s.n_target) * h->n_text_train);
+    return 0;
+}
+
+int fsar_episode_forward_host(fsar_handle* h, const fsar_episode* ep, float* logits_host, float* class_logits_host) {
+    RET_IF(fsar_episode_submit_host(h, 0, ep));
+    return fsar_episode_collect_host(h, 0, logits_host, class_logits_host);
+}
+
+int64_t fsar_peek(fsar_handle* h, const char* name, void* dst_host, int64_t numel, void* stream) {
+    if (h == nullptr || name == nullptr || dst_host == nullptr) return fail(h, FSAR_E_INVALID, "fsar_peek: NULL argument");
+    const int E = h->cfg.embed_dim, S = h->last_S, Q = h->last_Q, T = h->last_T, way = h->last_way;
+    const void* src = nullptr;
+    int64_t avail = 0;
+    size_t esz = sizeof(float);
+    const std::string n(name);
+    if (n == "support_feats") { src = h->feats; avail = (int64_t)S * T * E; }
+    else if (n == "target_feats") { src = h->feats + (size_t)S * T * E; avail = (int64_t)Q * T * E; }
+    else if (n == "mod_out") { src = h->mod_out; avail = (int64_t)h->last_rows * E; }
+    else if (n == "protos") { src = h->protos; avail = (int64_t)way * T * E; }
+    else if (n == "dists") { src = h->dists; avail = (int64_t)Q * way * T * T; }
+    else if (n == "cum_dists") { src = h->cum; avail = (int64_t)Q * way; }
+    else if (n == "class_index") { src = h->cls; avail = S; esz = sizeof(int); }
+    else return fail(h, FSAR_E_NAME, "unknown tap '%s'", name);
+    if (numel < avail) avail = numel;
+    CU_OK(h, cudaStreamSynchronize((cudaStream_t)stream));
+    if (h->compute_stream) CU_OK(h, cudaStreamSynchronize(h->compute_stream));
+    CU_OK(h, cudaMemcpy(dst_host, src, esz * (size_t)avail, cudaMemcpyDeviceToHost));
+    return avail;
+}
+
+int fsar_op_layernorm(fsar_handle* h, const float* x_dev, const float* gamma_dev, const float* beta_dev, int rows, int dim,
+                      int out16, void* out_dev, void* stream) {
+    if (h == nullptr || x_dev == nullptr || out_dev == nullptr || rows < 1) return fail(h, FSAR_E_INVALID, "fsar_op_layernorm: bad argument");
+    return layernorm(h, x_dev, out_dev, gamma_dev, beta_dev, rows, dim, out16 != 0, false, 1, nullptr, nullptr,
+                     (cudaStream_t)stream, FSAR_K_LAYERNORM);
+}
+
+int fsar_op_gemm(fsar_handle* h, const void* a16_dev, const void* w16_dev, const float* bias_dev, int M, int N, int K, int epi,
+                 void* out_dev, void* stream) {
+    if (h == nullptr || a16_dev == nullptr || w16_dev == nullptr || out_dev == nullptr) return fail(h, FSAR_E_INVALID, "fsar_op_gemm: NULL argument");
+    if (epi == EPI_PATCH32) return fail(h, FSAR_E_INVALID, "fsar_op_gemm: the patch epilogue is internal");
+    GemmParams p{};
+    p.bias = bias_dev; p.out = out_dev; p.ldo = N;
+    return gemm(h, FSAR_K_GEMM_QKV, (const T16*)a16_dev, (const T16*)w16_dev, M, N, K, epi, p, (cudaStream_t)stream);
+}
+
+int fsar_op_attention(fsar_handle* h, const void* qkv16_dev, int n_frames, int L, int heads, void* out16_dev, void* stream) {
+    if (h == nullptr || qkv16_dev == nullptr || out16_dev == nullptr || n_frames < 1 || L < 1 || heads < 1)
+        return fail(h, FSAR_E_INVALID, "fsar_op_attention: bad argument");
+    return attention(h, (const T16*)qkv16_dev, n_frames, L, heads, (T16*)out16_dev, (cudaStream_t)stream);
+}
+
+int fsar_op_f32_to_16(fsar_handle* h, const float* src_dev, void* dst16_dev, int64_t numel, void* stream) {
+    if (h == nullptr || src_dev == nullptr || dst16_dev == nullptr || numel < 1) return fail(h, FSAR_E_INVALID, "fsar_op_f32_to_16: bad argument");
+    const long long groups = (numel + 3) / 4;
+    Scope s(h, (cudaStream_t)stream, FSAR_K_HEAD_MISC, 0.0, 6.0 * numel);
+    f32_to_16_kernel<<<(int)((groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src_dev, (T16*)dst16_dev, numel);
+    return check_launch(h, "f32_to_16_kernel");
+}
+
+int64_t fsar_launch_count(const fsar_handle* h) { return h ? h->launches : -1; }
+
+int fsar_profile_begin(fsar_handle* h) {
+    if (h == nullptr) return FSAR_E_INVALID;
+    for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    h->prof.clear();
+    h->profiling = true;
+    return 0;
+}
+
+int fsar_profile_end(fsar_handle* h, fsar_profile* out) {
+    if (h == nullptr || out == nullptr) return fail(h, FSAR_E_INVALID, "fsar_profile_end: NULL argument");
+    h->profiling = false;
+    CU_OK(h, cudaDeviceSynchronize());
+    memset(out, 0, sizeof(*out));
+    for (auto& r : h->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        out->ms[r.cls] += ms;
+        out->launches[r.cls] += 1;
+        out->flops[r.cls] += r.flops;
+        out->bytes[r.cls] += r.bytes;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    h->prof.clear();
+    return 0;
+}
+
+}  // extern "C"

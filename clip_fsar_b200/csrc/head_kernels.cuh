@@ -1,0 +1,338 @@
+// fp32 kernels of the few-shot head: class/text logits, temporal prototype modulator (Transformer_v1),
+// per-class prototype means, cosine distance matrix and the OTAM soft-DTW dynamic program.
+// Reference semantics (all fp32): /root/reference/models/base/few_shot.py
+//   cos_sim 1115-1124, extract_class_indices 1127-1136, Transformer_v1 979-999, PreNormattention_qkv 971-977,
+//   Attention_qkv 1035-1073, FeedForward 1643-1654, OTAM_cum_dist_v2 2657-2687,
+//   CNN_OTAM_CLIPFSAR.forward eval branch 2932-2990.
+#pragma once
+#include "ptx.cuh"
+
+namespace fsar {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Class index of every support video: cls[s] = rank of labels[s] among the sorted distinct labels
+// (torch.unique(support_labels) is sorted, few_shot.py:2950/2960/2965); counts[c] = shots of class c.
+// Single CTA; S is small (way * shot).
+__global__ void class_index_kernel(const float* __restrict__ labels, int S, int* __restrict__ cls,
+                                   int* __restrict__ counts, int way) {
+    for (int c = threadIdx.x; c < way; c += blockDim.x) counts[c] = 0;
+    __syncthreads();
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        const long long ls = (long long)labels[s];  // .long() truncation
+        int rank = 0;
+        for (int a = 0; a < S; ++a) {
+            const long long la = (long long)labels[a];
+            if (la < ls) {
+                bool first = true;
+                for (int b = 0; b < a; ++b)
+                    if ((long long)labels[b] == la) { first = false; break; }
+                rank += first ? 1 : 0;
+            }
+        }
+        cls[s] = rank;
+        if (rank < way) atomicAdd(&counts[rank], 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// class_text_logits = cos_sim(mean_T(cat[support, target]), text_features_train) * scale  (few_shot.py:2937-2939)
+// One CTA per video.
+__global__ void __launch_bounds__(256)
+class_text_logits_kernel(const float* __restrict__ sup, int S, const float* __restrict__ tgt, int Q, int T, int E,
+                         const float* __restrict__ text, int C, const float* __restrict__ scale,
+                         float* __restrict__ out) {
+    extern __shared__ float sm[];  // [E]
+    __shared__ float red[8];
+    const int vid = blockIdx.x;
+    const float* src = (vid < S) ? sup + (size_t)vid * T * E : tgt + (size_t)(vid - S) * T * E;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float sq = 0.f;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        float a = 0.f;
+        for (int t = 0; t < T; ++t) a += src[(size_t)t * E + e];
+        a /= float(T);
+        sm[e] = a;
+        sq += a * a;
+    }
+    sq = warp_sum(sq);
+    if (lane == 0) red[warp] = sq;
+    __syncthreads();
+    float xn = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) xn += red[w];
+    xn = sqrtf(xn);
+    const float sc = scale[0];
+    for (int c = warp; c < C; c += (blockDim.x >> 5)) {
+        const float* tr = text + (size_t)c * E;
+        float dot = 0.f, tn = 0.f;
+        for (int e = lane; e < E; e += 32) {
+            const float tv = tr[e];
+            dot = fmaf(sm[e], tv, dot);
+            tn = fmaf(tv, tv, tn);
+        }
+        dot = warp_sum(dot);
+        tn = sqrtf(warp_sum(tn));
+        if (lane == 0) out[(size_t)vid * C + c] = dot / (xn * tn + 0.01f) * sc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Modulator input rows. Row layout of `seq` (fp32, [rows, E]):
+//   rows [0, Q*T)                          : query sequences (target features, T tokens each)
+//   rows [Q*T, Q*T + n_sup_seq * (T + 1))  : support sequences, T frame tokens + 1 text token
+// merge_before (TRAIN.MERGE_BEFORE, few_shot.py:2949-2954): n_sup_seq = way, tokens are per-class means over shots
+// (frames and text token alike); else n_sup_seq = S and the text token is text_test[real_support_labels[s]] (2946).
+__global__ void __launch_bounds__(128)
+build_sequences_kernel(const float* __restrict__ sup, const float* __restrict__ tgt, const float* __restrict__ text_test,
+                       const float* __restrict__ real_labels, const int* __restrict__ cls, const int* __restrict__ counts,
+                       int S, int Q, int T, int E, int way, int merge_before, float* __restrict__ seq) {
+    const int row = blockIdx.x;
+    const int qrows = Q * T;
+    float* dst = seq + (size_t)row * E;
+    if (row < qrows) {
+        for (int e = threadIdx.x; e < E; e += blockDim.x) dst[e] = tgt[(size_t)row * E + e];
+        return;
+    }
+    const int r = row - qrows;
+    const int sq = r / (T + 1), tok = r - sq * (T + 1);
+    if (!merge_before) {
+        const float* src = (tok < T) ? sup + ((size_t)sq * T + tok) * E
+                                     : text_test + (size_t)((long long)real_labels[sq]) * E;
+        for (int e = threadIdx.x; e < E; e += blockDim.x) dst[e] = src[e];
+    } else {
+        const float inv = 1.0f / float(counts[sq]);
+        for (int e = threadIdx.x; e < E; e += blockDim.x) {
+            float a = 0.f;
+            for (int s = 0; s < S; ++s) {
+                if (cls[s] == sq) {
+                    a += (tok < T) ? sup[((size_t)s * T + tok) * E + e]
+                                   : text_test[(size_t)((long long)real_labels[s]) * E + e];
+                }
+            }
+            dst[e] = a * inv;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 linear layer  C[R, N] = A[R, K] * W[N, K]^T (+ bias) (GELU) (+ residual).  SIMT, fp32 FMA:
+// the modulator is 3.1 M parameters and bound by reading them once; fp32 keeps parity with the
+// reference at ~1e-6. Tile 32 x 64, BK 32, 256 threads, 2 x 4 outputs per thread.
+enum LinAct : int { LIN_NONE = 0, LIN_GELU = 1 };
+constexpr int LIN_BM = 32, LIN_BN = 64, LIN_BK = 32;
+
+template <int ACT>
+__global__ void __launch_bounds__(256)
+linear_f32_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
+                  const float* residual, float* C, int R, int N, int K) {
+    __shared__ float sA[LIN_BK][LIN_BM + 1];
+    __shared__ float sW[LIN_BK][LIN_BN + 1];
+    const int r0 = blockIdx.y * LIN_BM, n0 = blockIdx.x * LIN_BN;
+    const int tid = threadIdx.x;
+    const int tr = tid >> 4;   // 0..15 -> rows tr*2, tr*2+1
+    const int tc = tid & 15;   // 0..15 -> cols tc + 16*j
+    float acc[2][4] = {};
+    for (int k0 = 0; k0 < K; k0 += LIN_BK) {
+        // A tile: 32 rows x 32 k
+        for (int i = tid; i < LIN_BM * LIN_BK; i += 256) {
+            const int r = i / LIN_BK, k = i - r * LIN_BK;
+            sA[k][r] = (r0 + r < R && k0 + k < K) ? A[(size_t)(r0 + r) * K + k0 + k] : 0.f;
+        }
+        for (int i = tid; i < LIN_BN * LIN_BK; i += 256) {
+            const int n = i / LIN_BK, k = i - n * LIN_BK;
+            sW[k][n] = (n0 + n < N && k0 + k < K) ? __ldg(W + (size_t)(n0 + n) * K + k0 + k) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < LIN_BK; ++k) {
+            const float a0 = sA[k][tr * 2], a1 = sA[k][tr * 2 + 1];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float w = sW[k][tc + 16 * j];
+                acc[0][j] = fmaf(a0, w, acc[0][j]);
+                acc[1][j] = fmaf(a1, w, acc[1][j]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int r = r0 + tr * 2 + i;
+        if (r >= R) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tc + 16 * j;
+            if (n >= N) continue;
+            float v = acc[i][j];
+            if (bias != nullptr) v += bias[n];
+            if (ACT == LIN_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));  // nn.GELU() exact
+            if (residual != nullptr) v += residual[(size_t)r * N + n];
+            C[(size_t)r * N + n] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Modulator attention (Attention_qkv.forward, few_shot.py:1055-1073): per (sequence, head)
+// softmax(q k^T * dim_head^-0.5) v over n_tok <= 33 tokens. q/k/v: [rows, inner] fp32, head h at h * dh.
+// `pitch` is the row pitch of q/k/v (they are column blocks of one fused [rows, 3 * inner] projection), o is [rows, inner].
+// Sequences: the first n_q have T tokens starting at row i * T; the following have T + 1 tokens.
+constexpr int MOD_MAX_TOK = 40;
+__global__ void __launch_bounds__(128)
+modulator_attention_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                           float* __restrict__ o, int n_q_seq, int T, int pitch, int inner, int dh, float scale) {
+    extern __shared__ float sm[];  // q[n][dh], k[n][dh], v[n][dh], p[n][n+1]
+    const int seq = blockIdx.x, head = blockIdx.y;
+    int row0, n;
+    if (seq < n_q_seq) { row0 = seq * T; n = T; }
+    else { row0 = n_q_seq * T + (seq - n_q_seq) * (T + 1); n = T + 1; }
+    float* sq = sm;
+    float* sk = sq + n * dh;
+    float* sv = sk + n * dh;
+    float* sp = sv + n * dh;
+    for (int i = threadIdx.x; i < n * dh; i += blockDim.x) {
+        const int t = i / dh, d = i - t * dh;
+        const size_t g = (size_t)(row0 + t) * pitch + head * dh + d;
+        sq[i] = q[g]; sk[i] = k[g]; sv[i] = v[g];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
+        const int a = i / n, b = i - a * n;
+        float dot = 0.f;
+        for (int d = 0; d < dh; ++d) dot = fmaf(sq[a * dh + d], sk[b * dh + d], dot);
+        sp[a * (n + 1) + b] = dot * scale;
+    }
+    __syncthreads();
+    for (int a = threadIdx.x; a < n; a += blockDim.x) {
+        float mx = -INFINITY;
+        for (int b = 0; b < n; ++b) mx = fmaxf(mx, sp[a * (n + 1) + b]);
+        float s = 0.f;
+        for (int b = 0; b < n; ++b) { const float e = expf(sp[a * (n + 1) + b] - mx); sp[a * (n + 1) + b] = e; s += e; }
+        const float inv = 1.0f / s;
+        for (int b = 0; b < n; ++b) sp[a * (n + 1) + b] *= inv;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * dh; i += blockDim.x) {
+        const int a = i / dh, d = i - a * dh;
+        float acc = 0.f;
+        for (int b = 0; b < n; ++b) acc = fmaf(sp[a * (n + 1) + b], sv[b * dh + d], acc);
+        o[(size_t)(row0 + a) * inner + head * dh + d] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Prototypes [way, T, E] from the modulated support sequences (first T tokens of each, few_shot.py:2956);
+// without MERGE_BEFORE the per-class mean over shots happens here (2959-2962).
+__global__ void __launch_bounds__(128)
+prototype_kernel(const float* __restrict__ mod_out, int q_rows, int n_sup_seq, int T, int E, const int* __restrict__ cls,
+                 const int* __restrict__ counts, int merge_before, float* __restrict__ protos) {
+    const int c = blockIdx.x / T, t = blockIdx.x - c * T;
+    float* dst = protos + ((size_t)c * T + t) * E;
+    if (merge_before) {
+        const float* src = mod_out + ((size_t)q_rows + (size_t)c * (T + 1) + t) * E;
+        for (int e = threadIdx.x; e < E; e += blockDim.x) dst[e] = src[e];
+    } else {
+        const float inv = 1.0f / float(counts[c]);
+        for (int e = threadIdx.x; e < E; e += blockDim.x) {
+            float a = 0.f;
+            for (int s = 0; s < n_sup_seq; ++s)
+                if (cls[s] == c) a += mod_out[((size_t)q_rows + (size_t)s * (T + 1) + t) * E + e];
+            dst[e] = a * inv;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cosine distances + OTAM.  One CTA per (query, class):
+//   dists[i][j] = 1 - q_i . p_j / (|q_i| |p_j| + 0.01)                      (cos_sim 1115-1124, 2973-2976)
+//   cum = OTAM(dists) (+ OTAM(dists^T) unless single_direct)                 (2657-2687, 2979-2982)
+//   logits[q][c] = -cum                                                      (2986-2989)
+// The DP runs as a wavefront: lane l owns row l; at step t it fills padded column m = t - l.
+constexpr int OTAM_MAX_T = 32;
+
+__device__ __forceinline__ float otam_wavefront(const float* d /*[T][T] smem, this direction: d[l*sl + m*sm]*/,
+                                                int sl, int sm_, int T, float lbda, float* c /*[T][T+2] smem*/,
+                                                int lane) {
+    const int W = T + 2;
+    if (lane < T) c[lane * W] = 0.f;  // column 0 stays 0
+    __syncwarp();
+    for (int t = 1; t <= (T - 1) + (T + 1); ++t) {
+        const int l = lane, m = t - l;
+        if (l < T && m >= 1 && m <= T + 1) {
+            const float dv = (m <= T) ? d[l * sl + (m - 1) * sm_] : 0.f;
+            float val;
+            if (l == 0) {
+                val = dv + c[m - 1];
+            } else {
+                const float* up = c + (l - 1) * W;
+                const float* cur = c + l * W;
+                float sum;
+                if (m == 1 || m == T + 1)
+                    sum = expf(-up[m - 1] / lbda) + expf(-up[m] / lbda) + expf(-cur[m - 1] / lbda);
+                else
+                    sum = expf(-up[m - 1] / lbda) + expf(-cur[m - 1] / lbda);
+                val = dv - lbda * logf(sum);
+            }
+            c[l * W + m] = val;
+        }
+        __syncwarp();
+    }
+    return c[(T - 1) * W + T + 1];
+}
+
+__global__ void __launch_bounds__(256)
+cos_otam_kernel(const float* __restrict__ qf /*[Q,T,E]*/, const float* __restrict__ pf /*[way,T,E]*/, int T, int E,
+                int way, float lbda, int single_direct, float* __restrict__ logits /*[Q,way]*/,
+                float* __restrict__ dists_out /*[Q,way,T,T] or null*/, float* __restrict__ cum_out /*[Q,way] or null*/) {
+    __shared__ float sd[OTAM_MAX_T * OTAM_MAX_T];
+    __shared__ float sqn[OTAM_MAX_T], spn[OTAM_MAX_T];
+    __shared__ float sc[2][OTAM_MAX_T * (OTAM_MAX_T + 2)];
+    __shared__ float sres[2];
+    const int qi = blockIdx.x, ci = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const float* qb = qf + (size_t)qi * T * E;
+    const float* pb = pf + (size_t)ci * T * E;
+    // norms
+    for (int i = warp; i < 2 * T; i += nw) {
+        const float* r = (i < T) ? qb + (size_t)i * E : pb + (size_t)(i - T) * E;
+        float s = 0.f;
+        for (int e = lane; e < E; e += 32) s = fmaf(r[e], r[e], s);
+        s = warp_sum(s);
+        if (lane == 0) { if (i < T) sqn[i] = sqrtf(s); else spn[i - T] = sqrtf(s); }
+    }
+    __syncthreads();
+    for (int ij = warp; ij < T * T; ij += nw) {
+        const int i = ij / T, j = ij - i * T;
+        const float* a = qb + (size_t)i * E;
+        const float* b = pb + (size_t)j * E;
+        float s = 0.f;
+        for (int e = lane; e < E; e += 32) s = fmaf(a[e], b[e], s);
+        s = warp_sum(s);
+        if (lane == 0) {
+            const float dist = 1.0f - s / (sqn[i] * spn[j] + 0.01f);
+            sd[ij] = dist;
+            if (dists_out != nullptr) dists_out[((size_t)qi * way + ci) * T * T + ij] = dist;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const float r = otam_wavefront(sd, T, 1, T, lbda, sc[0], lane);   // dists[l][m]
+        if (lane == 0) sres[0] = r;
+    } else if (warp == 1 && !single_direct) {
+        const float r = otam_wavefront(sd, 1, T, T, lbda, sc[1], lane);   // dists^T
+        if (lane == 0) sres[1] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float cum = single_direct ? sres[0] : sres[0] + sres[1];
+        if (cum_out != nullptr) cum_out[(size_t)qi * way + ci] = cum;
+        logits[(size_t)qi * way + ci] = -cum;
+    }
+}
+
+}  // namespace fsar

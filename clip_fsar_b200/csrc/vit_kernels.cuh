@@ -1,0 +1,365 @@
+// HBM-bound kernels of the CLIP ViT frame encoder (everything that is not a GEMM):
+//   patch gather (im2col + fp32->16-bit), LayerNorm (ln_pre / ln_1 / ln_2), ln_post + projection,
+//   and the per-(frame, head) softmax attention core.
+// Reference semantics: /root/reference/models/base/few_shot.py:605-611 (LayerNorm in fp32, eps 1e-5),
+// :671-688 (VisionTransformer.forward), :633-640 (ResidualAttentionBlock).
+#pragma once
+#include "ptx.cuh"
+#include "gemm_tcgen05.cuh"  // pack2<>
+
+namespace fsar {
+
+// ------------------------------------------------------------------------------------------------
+// Patch gather: frames NCHW fp32 [n, 3, S, S] -> A16 [n * G * G, Kp], k = c * P * P + ky * P + kx
+// (the flattening of conv1.weight [width, 3, P, P], few_shot.py:659,672). One thread per (frame, c, y, px):
+// it reads P contiguous floats and writes P contiguous 16-bit values. Columns [3 P P, Kp) are never
+// written; the buffer is zeroed once at creation.
+template <typename T16>
+__global__ void patch_gather_kernel(const float* __restrict__ frames, T16* __restrict__ out, int n_frames, int S,
+                                    int P, int Kp) {
+    const int G = S / P;
+    const long long total = (long long)n_frames * 3 * S * G;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int px = int(idx % G);
+    long long t = idx / G;
+    const int y = int(t % S);
+    t /= S;
+    const int c = int(t % 3);
+    const int n = int(t / 3);
+    const int py = y / P, ky = y - py * P;
+    const float* src = frames + (((size_t)n * 3 + c) * S + y) * S + (size_t)px * P;
+    T16* dst = out + ((size_t)n * G * G + (size_t)py * G + px) * Kp + (size_t)c * P * P + (size_t)ky * P;
+    if (P == 16) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        const float4 c4 = __ldg(reinterpret_cast<const float4*>(src) + 2);
+        const float4 d = __ldg(reinterpret_cast<const float4*>(src) + 3);
+        uint4 w0, w1;
+        w0.x = pack2<T16>(a.x, a.y); w0.y = pack2<T16>(a.z, a.w); w0.z = pack2<T16>(b.x, b.y); w0.w = pack2<T16>(b.z, b.w);
+        w1.x = pack2<T16>(c4.x, c4.y); w1.y = pack2<T16>(c4.z, c4.w); w1.z = pack2<T16>(d.x, d.y); w1.w = pack2<T16>(d.z, d.w);
+        reinterpret_cast<uint4*>(dst)[0] = w0;
+        reinterpret_cast<uint4*>(dst)[1] = w1;
+    } else {
+        // P even (14): 8-byte loads, 4-byte stores
+        for (int kx = 0; kx < P; kx += 2) {
+            const float2 a = __ldg(reinterpret_cast<const float2*>(src + kx));
+            *reinterpret_cast<uint32_t*>(dst + kx) = pack2<T16>(a.x, a.y);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the last dimension, one warp per row, statistics in fp32 (two-pass in registers).
+//   D % 128 == 0, D <= 1024.  OUT16: write T16, else write fp32 (may alias the input: in-place).
+//   CLS_FILL: rows whose token index (row % tokens) is 0 take class_embedding + positional_embedding[0]
+//   as their input instead of x (few_shot.py:675-677); other rows already hold conv1 + pos (GEMM epilogue).
+template <typename T16, bool OUT16, bool CLS_FILL>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* x, void* out, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 int rows, int D, float eps, int tokens, const float* __restrict__ cls_emb,
+                 const float* __restrict__ pos0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= rows) return;
+    const int nv = D >> 7;  // float4 per lane
+    float4 v[8];
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+    const bool is_cls = CLS_FILL && (row % tokens == 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (i < nv) {
+            if (is_cls) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(cls_emb) + lane + 32 * i);
+                const float4 b = __ldg(reinterpret_cast<const float4*>(pos0) + lane + 32 * i);
+                v[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+            } else {
+                v[i] = xr[lane + 32 * i];
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i < nv) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / float(D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i < nv) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = 1.0f / sqrtf(q / float(D) + eps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (i < nv) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+            float4 y;
+            y.x = (v[i].x - mean) * rstd * g.x + b.x;
+            y.y = (v[i].y - mean) * rstd * g.y + b.y;
+            y.z = (v[i].z - mean) * rstd * g.z + b.z;
+            y.w = (v[i].w - mean) * rstd * g.w + b.w;
+            if (OUT16) {
+                uint2 w;
+                w.x = pack2<T16>(y.x, y.y);
+                w.y = pack2<T16>(y.z, y.w);
+                reinterpret_cast<uint2*>(reinterpret_cast<T16*>(out) + (size_t)row * D)[lane + 32 * i] = w;
+            } else {
+                reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)row * D)[lane + 32 * i] = y;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ln_post(x[:, 0, :]) @ proj  (few_shot.py:683-686). One CTA handles FPC frames; proj is [D, E] fp32.
+constexpr int FINAL_FPC = 4;
+__global__ void __launch_bounds__(256)
+final_proj_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  const float* __restrict__ proj, float* __restrict__ out, int n_frames, int tokens, int D, int E,
+                  float eps) {
+    extern __shared__ float sm[];  // [FPC][D]
+    __shared__ float red[2][FINAL_FPC][8];
+    const int f0 = blockIdx.x * FINAL_FPC;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // load CLS rows
+    for (int f = 0; f < FINAL_FPC; ++f) {
+        const int fr = f0 + f;
+        for (int d = threadIdx.x; d < D; d += blockDim.x)
+            sm[f * D + d] = (fr < n_frames) ? x[(size_t)fr * tokens * D + d] : 0.f;
+    }
+    __syncthreads();
+    // mean
+    for (int f = 0; f < FINAL_FPC; ++f) {
+        float s = 0.f;
+        for (int d = threadIdx.x; d < D; d += blockDim.x) s += sm[f * D + d];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) red[0][f][warp] = s;
+    }
+    __syncthreads();
+    float mean[FINAL_FPC], rstd[FINAL_FPC];
+    for (int f = 0; f < FINAL_FPC; ++f) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += red[0][f][w];
+        mean[f] = s / float(D);
+    }
+    for (int f = 0; f < FINAL_FPC; ++f) {
+        float q = 0.f;
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            const float a = sm[f * D + d] - mean[f];
+            q += a * a;
+        }
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        if (lane == 0) red[1][f][warp] = q;
+    }
+    __syncthreads();
+    for (int f = 0; f < FINAL_FPC; ++f) {
+        float q = 0.f;
+        for (int w = 0; w < 8; ++w) q += red[1][f][w];
+        rstd[f] = 1.0f / sqrtf(q / float(D) + eps);
+    }
+    for (int f = 0; f < FINAL_FPC; ++f)
+        for (int d = threadIdx.x; d < D; d += blockDim.x)
+            sm[f * D + d] = (sm[f * D + d] - mean[f]) * rstd[f] * gamma[d] + beta[d];
+    __syncthreads();
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        float acc[FINAL_FPC];
+#pragma unroll
+        for (int f = 0; f < FINAL_FPC; ++f) acc[f] = 0.f;
+        for (int d = 0; d < D; ++d) {
+            const float w = __ldg(proj + (size_t)d * E + e);
+#pragma unroll
+            for (int f = 0; f < FINAL_FPC; ++f) acc[f] = fmaf(sm[f * D + d], w, acc[f]);
+        }
+#pragma unroll
+        for (int f = 0; f < FINAL_FPC; ++f)
+            if (f0 + f < n_frames) out[(size_t)(f0 + f) * E + e] = acc[f];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Attention core, register-resident softmax (warp-level mma.sync m16n8k16, fp32 accumulate).
+//   qkv16 [n_frames * L, 3 D] (row = frame * L + token; Q | K | V column blocks, head h at h * 64)
+//   out16 [n_frames * L, D]
+// One CTA = (64 query rows, head, frame); 4 warps x 16 query rows. Whole K/V of the (frame, head)
+// is staged in shared memory (L <= 16 * NKT keys), scores never touch HBM.
+// softmax(QK^T / sqrt(64)) V, no mask, no dropout (nn.MultiheadAttention in eval, few_shot.py:623,635).
+template <typename T16>
+struct MmaOp;
+template <>
+struct MmaOp<__half> {
+    __device__ static __forceinline__ void mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    }
+};
+template <>
+struct MmaOp<__nv_bfloat16> {
+    __device__ static __forceinline__ void mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    }
+};
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+
+constexpr int ATT_HD = 64;        // head dim (CLIP ViT-B/16, ViT-L/14: 64)
+constexpr int ATT_PITCH = 72;     // smem row pitch in 16-bit elements (144 B: conflict-free ldmatrix)
+constexpr int ATT_QROWS = 64;     // query rows per CTA
+
+template <int NKT>
+constexpr int att_smem_bytes() {
+    return (2 * NKT * 16 + ATT_QROWS) * ATT_PITCH * 2;
+}
+
+template <typename T16, int NKT>  // NKT = number of 16-key tiles staged (L <= 16 * NKT)
+__global__ void __launch_bounds__(128)
+attention_mma_kernel(const T16* __restrict__ qkv, T16* __restrict__ out, int L, int D, float scale_log2e) {
+    constexpr int LP = NKT * 16;
+    extern __shared__ __align__(16) uint8_t att_smem[];
+    T16* sK = reinterpret_cast<T16*>(att_smem);
+    T16* sV = sK + LP * ATT_PITCH;
+    T16* sQ = sV + LP * ATT_PITCH;
+
+    const int qblk = blockIdx.x, head = blockIdx.y, frame = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t row0 = (size_t)frame * L;
+    const int ld = 3 * D;
+    const T16* gq = qkv + row0 * ld + head * ATT_HD;
+    const T16* gk = gq + D;
+    const T16* gv = gq + 2 * D;
+
+    // ---- stage K, V (all keys) and this CTA's 64 query rows; rows >= L are zero
+    for (int i = threadIdx.x; i < LP * 8; i += blockDim.x) {
+        const int r = i >> 3, c = (i & 7) * 8;
+        uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+        if (r < L) {
+            kk = __ldg(reinterpret_cast<const uint4*>(gk + (size_t)r * ld + c));
+            vv = __ldg(reinterpret_cast<const uint4*>(gv + (size_t)r * ld + c));
+        }
+        *reinterpret_cast<uint4*>(sK + r * ATT_PITCH + c) = kk;
+        *reinterpret_cast<uint4*>(sV + r * ATT_PITCH + c) = vv;
+    }
+    for (int i = threadIdx.x; i < ATT_QROWS * 8; i += blockDim.x) {
+        const int r = i >> 3, c = (i & 7) * 8;
+        const int qr = qblk * ATT_QROWS + r;
+        uint4 qq = make_uint4(0, 0, 0, 0);
+        if (qr < L) qq = __ldg(reinterpret_cast<const uint4*>(gq + (size_t)qr * ld + c));
+        *reinterpret_cast<uint4*>(sQ + r * ATT_PITCH + c) = qq;
+    }
+    __syncthreads();
+
+    const int qrow_w = qblk * ATT_QROWS + warp * 16;  // first query row of this warp
+    if (qrow_w >= L) return;
+
+    // ---- Q fragments (A operand, 16 x 64): 4 k-steps x 4 regs
+    uint32_t qf[4][4];
+    {
+        const int r = warp * 16 + (lane & 15);
+        const int cofs = (lane >> 4) * 8;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) ldmatrix_x4(qf[kk], smem_u32(sQ + r * ATT_PITCH + kk * 16 + cofs));
+    }
+
+    // ---- S = Q K^T : NKT*2 n-tiles of 8 keys
+    float s[NKT * 2][4];
+#pragma unroll
+    for (int j = 0; j < NKT * 2; ++j) {
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+        uint32_t kb0[4], kb1[4];
+        const int key = j * 8 + (lane & 7);
+        const int cofs = (lane >> 3) * 8;
+        ldmatrix_x4(kb0, smem_u32(sK + key * ATT_PITCH + cofs));        // dims 0..31
+        ldmatrix_x4(kb1, smem_u32(sK + key * ATT_PITCH + 32 + cofs));   // dims 32..63
+        MmaOp<T16>::mma(s[j], qf[0], kb0[0], kb0[1]);
+        MmaOp<T16>::mma(s[j], qf[1], kb0[2], kb0[3]);
+        MmaOp<T16>::mma(s[j], qf[2], kb1[0], kb1[1]);
+        MmaOp<T16>::mma(s[j], qf[3], kb1[2], kb1[3]);
+    }
+
+    // ---- softmax over keys (rows g and g + 8 of this warp's 16), keys >= L masked
+    const int t4 = lane & 3;
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NKT * 2; ++j) {
+        const int k0 = j * 8 + t4 * 2;
+        if (k0 >= L) s[j][0] = s[j][2] = -INFINITY;
+        if (k0 + 1 >= L) s[j][1] = s[j][3] = -INFINITY;
+        mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float m0 = mx0 * scale_log2e, m1 = mx1 * scale_log2e;
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NKT * 2; ++j) {
+        s[j][0] = exp2f(s[j][0] * scale_log2e - m0);
+        s[j][1] = exp2f(s[j][1] * scale_log2e - m0);
+        s[j][2] = exp2f(s[j][2] * scale_log2e - m1);
+        s[j][3] = exp2f(s[j][3] * scale_log2e - m1);
+        sum0 += s[j][0] + s[j][1];
+        sum1 += s[j][2] + s[j][3];
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+
+    // ---- O = P V : P fragments come straight from the S accumulators
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < NKT; ++kt) {
+        uint32_t pa[4];
+        pa[0] = pack2<T16>(s[2 * kt][0], s[2 * kt][1]);
+        pa[1] = pack2<T16>(s[2 * kt][2], s[2 * kt][3]);
+        pa[2] = pack2<T16>(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+        pa[3] = pack2<T16>(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+        const int key = kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int cofs = (lane >> 4) * 8;
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {  // pairs of 8-wide d tiles
+            uint32_t vb[4];
+            ldmatrix_x4_trans(vb, smem_u32(sV + key * ATT_PITCH + np * 16 + cofs));
+            MmaOp<T16>::mma(o[2 * np], pa, vb[0], vb[1]);
+            MmaOp<T16>::mma(o[2 * np + 1], pa, vb[2], vb[3]);
+        }
+    }
+
+    // ---- normalise and store (row g: regs 0,1; row g + 8: regs 2,3)
+    const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+    const int g = lane >> 2;
+    const int r0 = qrow_w + g, r1 = r0 + 8;
+    T16* go = out + row0 * D + head * ATT_HD;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+        const int col = n * 8 + t4 * 2;
+        if (r0 < L) *reinterpret_cast<uint32_t*>(go + (size_t)r0 * D + col) = pack2<T16>(o[n][0] * inv0, o[n][1] * inv0);
+        if (r1 < L) *reinterpret_cast<uint32_t*>(go + (size_t)r1 * D + col) = pack2<T16>(o[n][2] * inv1, o[n][3] * inv1);
+    }
+}
+
+}  // namespace fsar

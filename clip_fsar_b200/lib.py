@@ -1,0 +1,356 @@
+"""ctypes binding of libfsar_sm100.so (C ABI in include/fsar.h).
+
+The reference (CLIP-FSAR) is pure Python and has no FFI of its own; this is the stub a maintainer adds to reach
+the sm_100a kernels from `models/base/few_shot.py`-style code. PyTorch is used only for
+device memory and streams: every call takes `tensor.data_ptr()` and `torch.cuda.current_stream().cuda_stream`.
+
+There is no fallback: a missing library or a missing sm_100 device raises.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+
+LIB_NAME = "libfsar_sm100.so"
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+
+FSAR_PROF_CLASSES = 12
+EPI_STORE16, EPI_QGELU16, EPI_RESID32, EPI_PATCH32, EPI_STORE32 = 0, 1, 2, 3, 4
+
+# every symbol include/fsar.h declares (tests check the library exports exactly these)
+SYMBOLS = [
+    "fsar_version", "fsar_class_name", "fsar_create", "fsar_destroy", "fsar_last_error", "fsar_set_weight",
+    "fsar_missing_weights", "fsar_missing_weight", "fsar_vit_forward", "fsar_modulate", "fsar_otam_logits",
+    "fsar_episode_forward", "fsar_episode_forward_host", "fsar_episode_submit_host", "fsar_episode_collect_host",
+    "fsar_peek", "fsar_operand_dtype", "fsar_op_layernorm", "fsar_op_gemm", "fsar_op_attention", "fsar_op_f32_to_16",
+    "fsar_launch_count", "fsar_profile_begin", "fsar_profile_end",
+]
+
+
+class FsarError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("libfsar_sm100 error %d: %s" % (code, message))
+        self.code = code
+
+
+class FsarConfig(Structure):
+    _fields_ = [
+        ("image_size", c_int32), ("patch_size", c_int32), ("width", c_int32), ("layers", c_int32),
+        ("heads", c_int32), ("embed_dim", c_int32), ("mod_heads", c_int32), ("mod_dim_head", c_int32),
+        ("mod_mlp_dim", c_int32), ("mod_depth", c_int32), ("max_frames", c_int32), ("max_videos", c_int32),
+        ("max_tokens", c_int32), ("max_classes", c_int32), ("otam_lambda", c_float), ("device", c_int32),
+    ]
+
+
+class FsarEpisode(Structure):
+    _fields_ = [
+        ("support_frames", c_void_p), ("target_frames", c_void_p), ("support_labels", c_void_p),
+        ("real_support_labels", c_void_p), ("n_support", c_int32), ("n_target", c_int32), ("n_frames", c_int32),
+        ("way", c_int32), ("merge_before", c_int32), ("single_direct", c_int32),
+    ]
+
+
+class FsarProfile(Structure):
+    _fields_ = [
+        ("ms", c_double * FSAR_PROF_CLASSES), ("launches", c_int64 * FSAR_PROF_CLASSES),
+        ("flops", c_double * FSAR_PROF_CLASSES), ("bytes", c_double * FSAR_PROF_CLASSES),
+    ]
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen the in-tree shared library and declare the prototypes. Raises if it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise FileNotFoundError(
+            "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(clip_fsar_b200/build.py); there is no CPU fallback" % p)
+    lib = ctypes.CDLL(p)
+    H = c_void_p
+    lib.fsar_version.restype = c_int
+    lib.fsar_class_name.restype = c_char_p
+    lib.fsar_class_name.argtypes = [c_int]
+    lib.fsar_create.argtypes = [POINTER(FsarConfig), POINTER(H)]
+    lib.fsar_destroy.argtypes = [H]
+    lib.fsar_destroy.restype = None
+    lib.fsar_last_error.argtypes = [H]
+    lib.fsar_last_error.restype = c_char_p
+    lib.fsar_set_weight.argtypes = [H, c_char_p, c_void_p, c_int64, c_int]
+    lib.fsar_missing_weights.argtypes = [H]
+    lib.fsar_missing_weight.argtypes = [H, c_int]
+    lib.fsar_missing_weight.restype = c_char_p
+    lib.fsar_vit_forward.argtypes = [H, c_void_p, c_int, c_void_p, c_void_p]
+    lib.fsar_modulate.argtypes = [H, c_void_p, c_int, c_int, c_void_p, c_void_p]
+    lib.fsar_otam_logits.argtypes = [H, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_void_p]
+    lib.fsar_episode_forward.argtypes = [H, POINTER(FsarEpisode), c_void_p, c_void_p, c_void_p]
+    lib.fsar_episode_forward_host.argtypes = [H, POINTER(FsarEpisode), c_void_p, c_void_p]
+    lib.fsar_episode_submit_host.argtypes = [H, c_int, POINTER(FsarEpisode)]
+    lib.fsar_episode_collect_host.argtypes = [H, c_int, c_void_p, c_void_p]
+    lib.fsar_peek.argtypes = [H, c_char_p, c_void_p, c_int64, c_void_p]
+    lib.fsar_peek.restype = c_int64
+    lib.fsar_operand_dtype.restype = c_int
+    lib.fsar_op_layernorm.argtypes = [H, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
+    lib.fsar_op_gemm.argtypes = [H, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
+    lib.fsar_op_attention.argtypes = [H, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
+    lib.fsar_op_f32_to_16.argtypes = [H, c_void_p, c_void_p, c_int64, c_void_p]
+    lib.fsar_launch_count.argtypes = [H]
+    lib.fsar_launch_count.restype = c_int64
+    lib.fsar_profile_begin.argtypes = [H]
+    lib.fsar_profile_end.argtypes = [H, POINTER(FsarProfile)]
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def geometry(backbone_name, num_frames=8, max_frames=None, max_videos=10, max_classes=128, mod_depth=1, device=0):
+    """fsar_config for the CLIP visual towers CNN_OTAM_CLIPFSAR can be built on (few_shot.py:2705-2713).
+    ViT-L/14 is an extension: the reference head has no branch for it (SURVEY.md headline finding 2)."""
+    table = {
+        "ViT-B/16": dict(image_size=224, patch_size=16, width=768, layers=12, heads=12, embed_dim=512),
+        "ViT-B/32": dict(image_size=224, patch_size=32, width=768, layers=12, heads=12, embed_dim=512),
+        "ViT-L/14": dict(image_size=224, patch_size=14, width=1024, layers=24, heads=16, embed_dim=768),
+    }
+    if backbone_name not in table:
+        raise ValueError("unsupported VIDEO.HEAD.BACKBONE_NAME %r (supported: %s)" % (backbone_name, sorted(table)))
+    g = dict(table[backbone_name])
+    g.update(mod_heads=8, mod_dim_head=g["embed_dim"] // 8, mod_mlp_dim=2048, mod_depth=int(mod_depth),
+             max_frames=int(max_frames or min(max_videos * num_frames, 384)), max_videos=int(max_videos),
+             max_tokens=int(num_frames), max_classes=int(max_classes), otam_lambda=0.5, device=int(device))
+    return g
+
+
+class Engine:
+    """One fsar_handle: owns packed weights + workspace on one device. Not thread-safe (one process per GPU)."""
+
+    def __init__(self, **cfg):
+        import torch  # device memory + streams only
+
+        self._torch = torch
+        self.lib = load_library()
+        self.cfg = FsarConfig(**cfg)
+        self._h = c_void_p()
+        rc = self.lib.fsar_create(byref(self.cfg), byref(self._h))
+        if rc != 0:
+            raise FsarError(rc, (self.lib.fsar_last_error(None) or b"").decode())
+        self.device = torch.device("cuda", self.cfg.device)
+        self.operand_dtype = torch.bfloat16 if self.lib.fsar_operand_dtype() == 1 else torch.float16
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.fsar_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise FsarError(rc, (self.lib.fsar_last_error(self._h) or b"").decode())
+
+    def _stream(self):
+        return c_void_p(self._torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _f32(self, t, name):
+        torch = self._torch
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError("%s must be a contiguous fp32 CUDA tensor (got %s %s)" % (name, t.dtype, t.device))
+        return c_void_p(t.data_ptr())
+
+    # ------------------------------------------------------------------ weights
+    def set_weight(self, name, tensor):
+        torch = self._torch
+        t = tensor.detach()
+        if t.dtype != torch.float32:
+            t = t.float()
+        t = t.contiguous()
+        self._check(self.lib.fsar_set_weight(self._h, name.encode(), c_void_p(t.data_ptr()), t.numel(),
+                                             1 if t.is_cuda else 0))
+
+    def load_state_dict(self, state, prefix=""):
+        """Push every tensor whose key (minus `prefix`) the library knows; returns the list of ignored keys."""
+        ignored = []
+        for k, v in state.items():
+            if not k.startswith(prefix):
+                ignored.append(k)
+                continue
+            try:
+                self.set_weight(k[len(prefix):], v)
+            except FsarError as e:
+                if e.code != -4:
+                    raise
+                ignored.append(k)
+        return ignored
+
+    def missing_weights(self):
+        n = self.lib.fsar_missing_weights(self._h)
+        return [self.lib.fsar_missing_weight(self._h, i).decode() for i in range(n)]
+
+    # ------------------------------------------------------------------ the path
+    def vit_forward(self, frames):
+        torch = self._torch
+        n = frames.shape[0]
+        out = torch.empty((n, self.cfg.embed_dim), dtype=torch.float32, device=self.device)
+        self._check(self.lib.fsar_vit_forward(self._h, self._f32(frames, "frames"), n, c_void_p(out.data_ptr()),
+                                              self._stream()))
+        return out
+
+    def modulate(self, x):
+        torch = self._torch
+        out = torch.empty_like(x)
+        self._check(self.lib.fsar_modulate(self._h, self._f32(x, "x"), x.shape[0], x.shape[1], c_void_p(out.data_ptr()),
+                                           self._stream()))
+        return out
+
+    def otam_logits(self, q, protos, single_direct=False, return_intermediates=False):
+        torch = self._torch
+        Q, T, _ = q.shape
+        way = protos.shape[0]
+        logits = torch.empty((Q, way), dtype=torch.float32, device=self.device)
+        dists = torch.empty((Q, way, T, T), dtype=torch.float32, device=self.device) if return_intermediates else None
+        cum = torch.empty((Q, way), dtype=torch.float32, device=self.device) if return_intermediates else None
+        self._check(self.lib.fsar_otam_logits(
+            self._h, self._f32(q, "q"), self._f32(protos, "protos"), Q, way, T, int(bool(single_direct)),
+            c_void_p(logits.data_ptr()), c_void_p(dists.data_ptr()) if dists is not None else None,
+            c_void_p(cum.data_ptr()) if cum is not None else None, self._stream()))
+        return (logits, dists, cum) if return_intermediates else logits
+
+    def _episode(self, support, target, support_labels, real_support_labels, n_frames, way, merge_before,
+                 single_direct):
+        S = support.shape[0] // n_frames
+        Q = target.shape[0] // n_frames
+        if S * n_frames != support.shape[0] or Q * n_frames != target.shape[0]:
+            raise ValueError("frame counts %d / %d are not multiples of NUM_INPUT_FRAMES=%d" %
+                             (support.shape[0], target.shape[0], n_frames))
+        if support_labels.numel() != S or real_support_labels.numel() != S:
+            raise ValueError("expected %d support labels, got %d / %d" %
+                             (S, support_labels.numel(), real_support_labels.numel()))
+        ep = FsarEpisode(support.data_ptr(), target.data_ptr(), support_labels.data_ptr(),
+                         real_support_labels.data_ptr(), S, Q, n_frames, way, int(bool(merge_before)),
+                         int(bool(single_direct)))
+        return ep, S, Q
+
+    def episode_forward(self, support, target, support_labels, real_support_labels, n_frames, way,
+                        merge_before=False, single_direct=False, n_train_classes=None, want_class_logits=True):
+        """Device-resident episode: returns (logits [Q, way], class_logits [S + Q, n_train] or None)."""
+        torch = self._torch
+        for name, t in (("support_set", support), ("target_set", target), ("support_labels", support_labels),
+                        ("real_support_labels", real_support_labels)):
+            self._f32(t, name)
+        ep, S, Q = self._episode(support, target, support_labels, real_support_labels, n_frames, way, merge_before,
+                                 single_direct)
+        logits = torch.empty((Q, way), dtype=torch.float32, device=self.device)
+        cl = None
+        if want_class_logits:
+            cl = torch.empty((S + Q, int(n_train_classes)), dtype=torch.float32, device=self.device)
+        self._check(self.lib.fsar_episode_forward(self._h, byref(ep), c_void_p(logits.data_ptr()),
+                                                  c_void_p(cl.data_ptr()) if cl is not None else None,
+                                                  self._stream()))
+        return logits, cl
+
+    def _host_episode(self, support, target, support_labels, real_support_labels, n_frames, way, merge_before,
+                      single_direct):
+        torch = self._torch
+        for name, t in (("support_set", support), ("target_set", target), ("support_labels", support_labels),
+                        ("real_support_labels", real_support_labels)):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("%s must be a contiguous fp32 HOST tensor" % name)
+        return self._episode(support, target, support_labels, real_support_labels, n_frames, way, merge_before,
+                             single_direct)
+
+    def episode_submit_host(self, slot, support, target, support_labels, real_support_labels, n_frames, way,
+                            merge_before=False, single_direct=False):
+        ep, S, Q = self._host_episode(support, target, support_labels, real_support_labels, n_frames, way,
+                                      merge_before, single_direct)
+        self._check(self.lib.fsar_episode_submit_host(self._h, slot, byref(ep)))
+        return S, Q
+
+    def episode_collect_host(self, slot, logits_out, class_logits_out=None):
+        self._check(self.lib.fsar_episode_collect_host(
+            self._h, slot, c_void_p(logits_out.data_ptr()),
+            c_void_p(class_logits_out.data_ptr()) if class_logits_out is not None else None))
+
+    def episode_forward_host(self, support, target, support_labels, real_support_labels, n_frames, way,
+                             merge_before=False, single_direct=False, n_train_classes=0):
+        """HOST buffers in, HOST results out; H2D/D2H copies happen inside the call (runs/test_net_few_shot.py:61-62
+        + the .item() reads at 174-178)."""
+        torch = self._torch
+        S, Q = self.episode_submit_host(0, support, target, support_labels, real_support_labels, n_frames, way,
+                                        merge_before, single_direct)
+        logits = torch.empty((Q, way), dtype=torch.float32)
+        cl = torch.empty((S + Q, int(n_train_classes)), dtype=torch.float32) if n_train_classes else None
+        self.episode_collect_host(0, logits, cl)
+        return logits, cl
+
+    def peek(self, name, shape, dtype=None):
+        torch = self._torch
+        out = torch.empty(shape, dtype=dtype or torch.float32)
+        n = self.lib.fsar_peek(self._h, name.encode(), c_void_p(out.data_ptr()), out.numel(), self._stream())
+        if n < 0:
+            self._check(int(n))
+        if n != out.numel():
+            raise FsarError(-1, "tap %s holds %d elements, asked for %d" % (name, n, out.numel()))
+        return out
+
+    # ------------------------------------------------------------------ single operators (parity tests)
+    def op_f32_to_16(self, x):
+        torch = self._torch
+        out = torch.empty(x.shape, dtype=self.operand_dtype, device=self.device)
+        self._check(self.lib.fsar_op_f32_to_16(self._h, self._f32(x, "x"), c_void_p(out.data_ptr()), x.numel(),
+                                               self._stream()))
+        return out
+
+    def op_layernorm(self, x, gamma, beta, out16=False):
+        torch = self._torch
+        rows, dim = x.shape
+        out = torch.empty((rows, dim), dtype=self.operand_dtype if out16 else torch.float32, device=self.device)
+        self._check(self.lib.fsar_op_layernorm(self._h, self._f32(x, "x"), self._f32(gamma, "gamma"),
+                                               self._f32(beta, "beta"), rows, dim, int(out16),
+                                               c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def op_gemm(self, a16, w16, bias=None, epi=EPI_STORE32, out=None):
+        torch = self._torch
+        M, K = a16.shape
+        N, K2 = w16.shape
+        if K != K2 or a16.dtype != self.operand_dtype or w16.dtype != self.operand_dtype:
+            raise ValueError("op_gemm: A [M,K] and W [N,K] must share K and be %s" % self.operand_dtype)
+        if out is None:
+            dt = self.operand_dtype if epi in (EPI_STORE16, EPI_QGELU16) else torch.float32
+            out = torch.zeros((M, N), dtype=dt, device=self.device)
+        self._check(self.lib.fsar_op_gemm(self._h, c_void_p(a16.data_ptr()), c_void_p(w16.data_ptr()),
+                                          self._f32(bias, "bias") if bias is not None else None, M, N, K, epi,
+                                          c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def op_attention(self, qkv16, n_frames, L, heads):
+        torch = self._torch
+        out = torch.empty((n_frames * L, heads * 64), dtype=self.operand_dtype, device=self.device)
+        self._check(self.lib.fsar_op_attention(self._h, c_void_p(qkv16.data_ptr()), n_frames, L, heads,
+                                               c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ instrumentation
+    def launch_count(self):
+        return int(self.lib.fsar_launch_count(self._h))
+
+    def profile_begin(self):
+        self._check(self.lib.fsar_profile_begin(self._h))
+
+    def profile_end(self):
+        prof = FsarProfile()
+        self._check(self.lib.fsar_profile_end(self._h, byref(prof)))
+        out = {}
+        for k in range(FSAR_PROF_CLASSES):
+            if prof.launches[k]:
+                out[self.lib.fsar_class_name(k).decode()] = dict(ms=prof.ms[k], launches=int(prof.launches[k]),
+                                                                 flops=prof.flops[k], bytes=prof.bytes[k])
+        return out

@@ -1,0 +1,160 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run here (the container that has /root/reference); the GPU box only sees the committed fixtures:
+    python oracle/gen_golden.py [--only NAME]
+
+What is real reference code: models.base.few_shot.{CLIP, VisionTransformer, Transformer_v1, cos_sim,
+OTAM_cum_dist_v2, CNN_OTAM_CLIPFSAR.forward} and models.base.models.BaseVideoModel, imported as they lie.
+What is patched: `ipdb` / `ftfy` stubs; `few_shot.load` returns a random-init CLIP of the requested
+geometry instead of downloading a checkpoint; `Tensor.cuda` is the identity on this CPU-only box; the seeded
+synthetic state_dict (clip_fsar_b200/synth.py) is loaded with strict=True (which also pins the parameter names);
+text_features_{train,test} (plain attributes, few_shot.py:2720/2728) are overwritten with seeded arrays because
+the text tower is init-time only and out of scope; for non-ViT-B/16 geometries `context2` is rebuilt with the
+reference's own Transformer_v1 class at the right width (the reference hard-codes mid_dim = 512, few_shot.py:2713).
+"""
+import argparse
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+from clip_fsar_b200 import synth  # noqa: E402
+
+CASES = {
+    # name: geometry, way, shot, T, flags, weight seed, episode seed
+    "tiny_5w1s": dict(geom="tiny", way=5, shot=1, T=8),
+    "tiny_5w5s_merge": dict(geom="tiny", way=5, shot=5, T=8, merge_before=True),
+    "tiny_5w5s_nomerge": dict(geom="tiny", way=5, shot=5, T=8),
+    "tiny_10w1s_T16": dict(geom="tiny", way=10, shot=1, T=16),
+    "tiny_3w2s_T32_single": dict(geom="tiny", way=3, shot=2, T=32, single_direct=True),
+    "tiny_5w1s_depth2": dict(geom="tiny", way=5, shot=1, T=8, mod_depth=2),
+    "tiny_5w1s_default_init": dict(geom="tiny", way=5, shot=1, T=8, spread=False, structured=False),
+    "small_5w1s": dict(geom="small", way=5, shot=1, T=8),
+    "vitb16_5w1s": dict(geom="ViT-B/16", way=5, shot=1, T=8),
+}
+
+
+def import_reference():
+    def stub(name, **kw):
+        m = types.ModuleType(name)
+        m.__dict__.update(kw)
+        sys.modules[name] = m
+        return m
+
+    stub("ipdb", set_trace=lambda *a, **k: None)
+    stub("ftfy", fix_text=lambda s: s)
+    sys.path.insert(0, REF)
+    import models.base.few_shot as fs
+    from models.base.models import BaseVideoModel
+    if not torch.cuda.is_available():
+        torch.Tensor.cuda = lambda self, *a, **k: self
+    return fs, BaseVideoModel
+
+
+def build_reference(fs, BaseVideoModel, g, n_train, n_test, T, flags):
+    heads = g["width"] // 64
+    assert heads == g["heads"]
+    fs.load = lambda name, cfg=None, device="cpu", jit=False, **kw: (
+        fs.CLIP(g["embed_dim"], g["image_size"], g["layers"], g["width"], g["patch_size"], 77, 49408, 64, 1, 1)
+        .float().eval(), None)
+    NS = types.SimpleNamespace
+    train = NS(CLASS_NAME=["c%d" % i for i in range(n_train)], WAY=5, SHOT=1, BATCH_SIZE=1)
+    if flags.get("merge_before"):
+        train.MERGE_BEFORE = True
+    if flags.get("single_direct"):
+        train.SINGLE_DIRECT = True
+    if flags.get("mod_depth", 1) > 1:
+        train.TRANSFORMER_DEPTH = flags["mod_depth"]
+    cfg = NS(TRAIN=train, TEST=NS(CLASS_NAME=["t%d" % i for i in range(n_test)]), DATA=NS(NUM_INPUT_FRAMES=T),
+             VIDEO=NS(HEAD=NS(NAME="CNN_OTAM_CLIPFSAR", BACKBONE_NAME="ViT-B/16"), BACKBONE=NS(META_ARCH="Identity")),
+             BN=NS(FREEZE=False))
+    model = BaseVideoModel(cfg)
+    head = model.head
+    if g["embed_dim"] != 512:
+        head.mid_dim = g["embed_dim"]
+        head.context2 = fs.Transformer_v1(dim=g["embed_dim"], heads=8, dim_head_k=g["embed_dim"] // 8, dropout_atte=0.2,
+                                          depth=flags.get("mod_depth", 1))
+    return model.eval()
+
+
+def run_case(name, fs, BaseVideoModel, out_dir):
+    case = dict(CASES[name])
+    g = synth.full_geometry(case["geom"], case.get("mod_depth", 1))
+    way, shot, T = case["way"], case["shot"], case["T"]
+    n_train, n_test = 64, 24
+    wseed, eseed = case.get("wseed", 0), case.get("eseed", 1000)
+    sd = synth.synth_state_dict(g, seed=wseed, spread=case.get("spread", True))
+    text_train = synth.synth_text_features(n_train, g["embed_dim"], seed=7)
+    text_test = synth.synth_text_features(n_test, g["embed_dim"], seed=8)
+    task = synth.synth_episode(way, shot, 1, T, g["image_size"], n_test, seed=eseed, structured=case.get("structured", True))
+
+    model = build_reference(fs, BaseVideoModel, g, n_train, n_test, T, case)
+    head = model.head
+    missing = head.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    head.text_features_train = torch.from_numpy(text_train)
+    head.text_features_test = torch.from_numpy(text_test)
+
+    taps = {"backbone": [], "context2": [], "dists": []}
+    h1 = head.backbone.register_forward_hook(lambda m, i, o: taps["backbone"].append(o.detach().clone()))
+    h2 = head.context2.register_forward_hook(lambda m, i, o: taps["context2"].append(o.detach().clone()))
+    orig_otam = fs.OTAM_cum_dist_v2
+
+    def rec_otam(d, lbda=0.5):
+        taps["dists"].append(d.detach().clone())
+        return orig_otam(d, lbda)
+
+    fs.OTAM_cum_dist_v2 = rec_otam
+    try:
+        with torch.no_grad():
+            out = model({k: torch.from_numpy(v) for k, v in task.items()})
+    finally:
+        fs.OTAM_cum_dist_v2 = orig_otam
+        h1.remove()
+        h2.remove()
+
+    E = g["embed_dim"]
+    meta = dict(case=name, geom=case["geom"], way=way, shot=shot, T=T, n_train=n_train, n_test=n_test, wseed=wseed,
+                eseed=eseed, spread=case.get("spread", True), structured=case.get("structured", True),
+                merge_before=bool(case.get("merge_before")), single_direct=bool(case.get("single_direct")),
+                mod_depth=case.get("mod_depth", 1), text_seeds=[7, 8], reference_commit="30cf0a8c",
+                torch=torch.__version__, state_dict_keys=sorted(head.state_dict().keys()))
+    arrays = dict(
+        logits=out["logits"].numpy(), class_logits=out["class_logits"].numpy(),
+        support_feats=taps["backbone"][0].reshape(-1, T, E).numpy(), target_feats=taps["backbone"][1].reshape(-1, T, E).numpy(),
+        target_mod=taps["context2"][0].numpy(), support_mod=taps["context2"][1].numpy(), dists=taps["dists"][0].numpy(),
+        # checksums of the regenerated inputs so a test can tell "generator drifted" from "oracle is wrong"
+        weight_checksum=np.array([float(np.sum([np.float64(v).sum() for v in sd.values()]))]),
+        input_checksum=np.array([float(np.float64(task["support_set"]).sum() + np.float64(task["target_set"]).sum())]),
+    )
+    path = os.path.join(out_dir, name + ".npz")
+    np.savez_compressed(path, meta=np.array(json.dumps(meta)), **arrays)
+    lg = arrays["logits"]
+    print("%-26s logits mean %.4f row-spread %.4f argmax %s  -> %s (%d KB)" % (
+        name, lg.mean(), (lg.max(1) - lg.min(1)).mean(), lg.argmax(1).tolist(), path, os.path.getsize(path) // 1024))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
+    a = ap.parse_args()
+    os.makedirs(a.out, exist_ok=True)
+    cwd = os.getcwd()
+    fs, BaseVideoModel = import_reference()
+    os.chdir(cwd)
+    for name in CASES:
+        if a.only and name != a.only:
+            continue
+        run_case(name, fs, BaseVideoModel, a.out)
+
+
+if __name__ == "__main__":
+    main()
