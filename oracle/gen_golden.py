@@ -38,6 +38,8 @@ CASES = {
     "tiny_5w1s_default_init": dict(geom="tiny", way=5, shot=1, T=8, spread=False, structured=False),
     "small_5w1s": dict(geom="small", way=5, shot=1, T=8),
     "vitb16_5w1s": dict(geom="ViT-B/16", way=5, shot=1, T=8),
+    # the configuration BASELINE.json names: ViT-B/16 "random-init" (default-style init, unstructured N(0,1) frames)
+    "vitb16_5w1s_default_init": dict(geom="ViT-B/16", way=5, shot=1, T=8, spread=False, structured=False, eseed=1001),
 }
 
 
