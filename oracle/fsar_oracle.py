@@ -50,41 +50,56 @@ def patchify(frames, P):
     return x.reshape(n, G * G, C * P * P)
 
 
-def residual_block(x, sd, p, heads):
+def _rnd(x, dt):
+    """Round to the tensor-core operand type and back (emulates the 16-bit operand storage of the CUDA path)."""
+    return x if dt is None else x.to(dt).float()
+
+
+def residual_block(x, sd, p, heads, dt=None):
     """ResidualAttentionBlock.forward, few_shot.py:633-640 with nn.MultiheadAttention(d, heads) (623, 635):
-    no mask, no dropout in eval, head_dim ** -0.5 scaling of q. x: [n, L, D]."""
+    no mask, no dropout in eval, head_dim ** -0.5 scaling of q. x: [n, L, D].
+    dt != None additionally rounds every GEMM operand to that 16-bit type exactly where the CUDA path stores one
+    (LN outputs, weights, QKV, softmax numerators, attention output, GELU output); accumulation, residual stream,
+    LN / softmax statistics stay fp32 in both."""
     n, L, D = x.shape
     dh = D // heads
-    y = layer_norm(x, sd[p + "ln_1.weight"], sd[p + "ln_1.bias"])
-    qkv = y @ sd[p + "attn.in_proj_weight"].T + sd[p + "attn.in_proj_bias"]
+    y = _rnd(layer_norm(x, sd[p + "ln_1.weight"], sd[p + "ln_1.bias"]), dt)
+    qkv = _rnd(y @ _rnd(sd[p + "attn.in_proj_weight"], dt).T + sd[p + "attn.in_proj_bias"], dt)
     q, k, v = qkv.split(D, dim=-1)
     q = q.reshape(n, L, heads, dh).transpose(1, 2)
     k = k.reshape(n, L, heads, dh).transpose(1, 2)
     v = v.reshape(n, L, heads, dh).transpose(1, 2)
-    att = torch.softmax((q * dh ** -0.5) @ k.transpose(-1, -2), dim=-1)
-    o = (att @ v).transpose(1, 2).reshape(n, L, D)
-    x = x + o @ sd[p + "attn.out_proj.weight"].T + sd[p + "attn.out_proj.bias"]
-    y = layer_norm(x, sd[p + "ln_2.weight"], sd[p + "ln_2.bias"])
-    hdn = quick_gelu(y @ sd[p + "mlp.c_fc.weight"].T + sd[p + "mlp.c_fc.bias"])
-    return x + hdn @ sd[p + "mlp.c_proj.weight"].T + sd[p + "mlp.c_proj.bias"]
+    s = (q @ k.transpose(-1, -2)) * dh ** -0.5
+    if dt is None:
+        o = torch.softmax(s, dim=-1) @ v
+    else:  # un-normalised numerators are the 16-bit P operand; the fp32 row sum divides afterwards
+        e = torch.exp(s - s.max(-1, keepdim=True).values)
+        o = (_rnd(e, dt) @ v) / e.sum(-1, keepdim=True)
+    o = _rnd(o.transpose(1, 2).reshape(n, L, D), dt)
+    x = x + o @ _rnd(sd[p + "attn.out_proj.weight"], dt).T + sd[p + "attn.out_proj.bias"]
+    y = _rnd(layer_norm(x, sd[p + "ln_2.weight"], sd[p + "ln_2.bias"]), dt)
+    hdn = _rnd(quick_gelu(y @ _rnd(sd[p + "mlp.c_fc.weight"], dt).T + sd[p + "mlp.c_fc.bias"]), dt)
+    return x + hdn @ _rnd(sd[p + "mlp.c_proj.weight"], dt).T + sd[p + "mlp.c_proj.bias"]
 
 
-def vit_forward(sd, g, frames, taps=None, chunk=16):
-    """VisionTransformer.forward, few_shot.py:671-688: frames [n,3,S,S] -> [n, embed_dim]."""
+def vit_forward(sd, g, frames, taps=None, chunk=16, operand_dtype=None):
+    """VisionTransformer.forward, few_shot.py:671-688: frames [n,3,S,S] -> [n, embed_dim].
+    operand_dtype=torch.float16 emulates the CUDA path's operand rounding (see residual_block)."""
     sd = {k: _t(v) for k, v in sd.items()}
     frames = _t(frames).float()
+    dt = operand_dtype
     D, P = g["width"], g["patch_size"]
     outs = []
     for s in range(0, frames.shape[0], chunk):
         f = frames[s:s + chunk]
-        x = patchify(f, P) @ sd["backbone.conv1.weight"].reshape(D, -1).T                       # 672-674
+        x = _rnd(patchify(f, P), dt) @ _rnd(sd["backbone.conv1.weight"].reshape(D, -1), dt).T    # 672-674
         cls = sd["backbone.class_embedding"].expand(x.shape[0], 1, D)                         # 675
         x = torch.cat([cls, x], dim=1) + sd["backbone.positional_embedding"]                  # 675-676
         x = layer_norm(x, sd["backbone.ln_pre.weight"], sd["backbone.ln_pre.bias"])           # 677
         if taps is not None and s == 0:
             taps["ln_pre"] = x.clone()
         for i in range(g["layers"]):                                                           # 679-681
-            x = residual_block(x, sd, "backbone.transformer.resblocks.%d." % i, g["heads"])
+            x = residual_block(x, sd, "backbone.transformer.resblocks.%d." % i, g["heads"], dt)
             if taps is not None and s == 0:
                 taps["block%d" % i] = x.clone()
         x = layer_norm(x[:, 0, :], sd["backbone.ln_post.weight"], sd["backbone.ln_post.bias"])  # 683
@@ -201,10 +216,10 @@ def head_forward(sd, g, text_train, text_test, support_feats, target_feats, supp
 
 
 def episode_forward(sd, g, text_train, text_test, task, n_frames, merge_before=False, single_direct=False,
-                    lbda=0.5):
+                    lbda=0.5, operand_dtype=None):
     """CNN_OTAM_CLIPFSAR.forward (eval), few_shot.py:2772-2990, on a task dict of numpy arrays / tensors."""
-    sup = vit_forward(sd, g, task["support_set"])                                         # get_feats 2760-2765
-    tgt = vit_forward(sd, g, task["target_set"])
+    sup = vit_forward(sd, g, task["support_set"], operand_dtype=operand_dtype)            # get_feats 2760-2765
+    tgt = vit_forward(sd, g, task["target_set"], operand_dtype=operand_dtype)
     E = sup.shape[-1]
     out = head_forward(sd, g, text_train, text_test, sup.reshape(-1, n_frames, E), tgt.reshape(-1, n_frames, E),
                        task["support_labels"], task["real_support_labels"], merge_before, single_direct, lbda)

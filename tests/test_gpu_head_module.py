@@ -1,0 +1,42 @@
+"""GPU: the registered nn.Module (the drop-in boundary) drives the same C-ABI path and agrees with the fixtures."""
+import types
+
+import pytest
+import torch
+
+from conftest import load_golden, regenerate
+from test_head_module import make_cfg
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,flags", [("tiny_5w1s", {}), ("tiny_5w5s_merge", {"MERGE_BEFORE": True}),
+                                        ("tiny_3w2s_T32_single", {"SINGLE_DIRECT": True}),
+                                        ("tiny_5w1s_depth2", {"TRANSFORMER_DEPTH": 2})])
+def test_module_forward_matches_reference_fixture(name, flags):
+    from clip_fsar_b200.head import CNN_OTAM_CLIPFSAR_SM100
+    meta, ref = load_golden(name)
+    g, sd, tt, te, task = regenerate(meta)
+    head = CNN_OTAM_CLIPFSAR_SM100(make_cfg(backbone=meta["geom"], T=meta["T"], **flags), torch.from_numpy(tt),
+                                   torch.from_numpy(te)).cuda().eval()
+    head.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    dev = {k: torch.from_numpy(v).cuda() for k, v in task.items()}
+    with torch.no_grad():
+        out = head(dev)
+    assert set(out) == {"logits", "class_logits"}
+    assert out["logits"].is_cuda and out["logits"].shape == ref["logits"].shape
+    err = (out["logits"].cpu() - torch.from_numpy(ref["logits"])).abs().max() / abs(ref["logits"]).max()
+    assert float(err) < 3e-3
+    assert (out["logits"].cpu().numpy().argmax(1) == ref["logits"].argmax(1)).all()
+    # way falls back to torch.unique when batch_class_list is absent (few_shot.py:2965)
+    dev.pop("batch_class_list")
+    with torch.no_grad():
+        again = head(dev)
+    assert torch.equal(again["logits"], out["logits"])
+    # parameter updates reach the engine (version counters), e.g. after loading another checkpoint
+    with torch.no_grad():
+        head.scale.mul_(2.0)
+        scaled = head(dev)
+    assert torch.allclose(scaled["class_logits"], 2.0 * out["class_logits"], rtol=1e-5, atol=1e-7)
+    loss = head.loss({"target_labels": dev["target_labels"]}, out)
+    assert torch.isfinite(loss)

@@ -1,0 +1,80 @@
+"""CPU: the oracle restatement against the fixtures produced by the reference's own forward (oracle/gen_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden, regenerate
+from oracle import fsar_oracle as O
+
+FAST = [n for n in golden_names() if not n.startswith("vitb16")]
+FULL = [n for n in golden_names() if n.startswith("vitb16")]
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a) - b).max() / (np.abs(b).max() + 1e-30))
+
+
+@pytest.mark.parametrize("name", FAST + FULL[:1])
+def test_oracle_matches_reference_outputs(name):
+    meta, ref = load_golden(name)
+    g, sd, tt, te, task = regenerate(meta)
+    # the regenerated inputs are the ones the reference saw
+    assert np.isclose(sum(np.float64(v).sum() for v in sd.values()), ref["weight_checksum"][0], rtol=0, atol=1e-6)
+    assert np.isclose(np.float64(task["support_set"]).sum() + np.float64(task["target_set"]).sum(),
+                      ref["input_checksum"][0], rtol=0, atol=1e-6)
+    out = O.episode_forward(sd, g, tt, te, task, meta["T"], meta["merge_before"], meta["single_direct"])
+    # fp32 vs fp32: only summation-order noise is allowed
+    assert rel(out["support_feats"], ref["support_feats"]) < 2e-5
+    assert rel(out["target_feats"], ref["target_feats"]) < 2e-5
+    assert rel(out["target_mod"], ref["target_mod"]) < 2e-5
+    assert rel(out["dists"], ref["dists"]) < 1e-5
+    assert rel(out["logits"], ref["logits"]) < 1e-5
+    assert rel(out["class_logits"], ref["class_logits"]) < 1e-5
+    assert (out["logits"].numpy().argmax(1) == ref["logits"].argmax(1)).all()
+
+
+def test_state_dict_names_match_reference():
+    from clip_fsar_b200 import synth
+    for name in ("tiny_5w1s", "tiny_5w1s_depth2", "vitb16_5w1s"):
+        meta, _ = load_golden(name)
+        g = synth.full_geometry(meta["geom"], meta["mod_depth"])
+        assert sorted(synth.state_dict_shapes(g)) == meta["state_dict_keys"]
+
+
+@pytest.mark.parametrize("T", [1, 2, 8, 16, 32])
+def test_otam_vectorised_equals_scalar_recurrence(T):
+    rng = np.random.default_rng(T)
+    d = rng.random((3, 4, T, T)).astype(np.float32) * 1.5
+    cum = O.otam_cum_dist(d).numpy()
+    for q in range(3):
+        for c in range(4):
+            assert abs(cum[q, c] - O.otam_scalar(d[q, c])) < 1e-4 * max(1.0, abs(cum[q, c]))
+
+
+def test_otam_ragged_direction_shapes():
+    # OTAM_cum_dist_v2 accepts non-square [T, T'] matrices (query and support lengths differ)
+    d = np.random.default_rng(0).random((2, 2, 5, 9)).astype(np.float32)
+    cum = O.otam_cum_dist(d).numpy()
+    assert cum.shape == (2, 2)
+    assert abs(cum[1, 0] - O.otam_scalar(d[1, 0])) < 1e-4
+
+
+def test_cos_sim_epsilon_on_product_of_norms():
+    x = torch.tensor([[3.0, 4.0]])
+    y = torch.tensor([[3.0, 4.0], [0.0, 0.0]])
+    s = O.cos_sim(x, y)
+    assert abs(float(s[0, 0]) - 25.0 / 25.01) < 1e-6
+    assert float(s[0, 1]) == 0.0  # zero vector: 0 / (0 + 0.01), no NaN
+
+
+def test_class_index_sorted_unique():
+    cls, way = O.class_index(np.array([7.0, 2.0, 7.0, 5.0, 2.0], dtype=np.float32))
+    assert way == 3 and cls.tolist() == [2, 0, 2, 1, 0]
+
+
+def test_operand16_emulation_is_close_to_fp32():
+    meta, ref = load_golden("tiny_5w1s")
+    g, sd, tt, te, task = regenerate(meta)
+    out = O.episode_forward(sd, g, tt, te, task, meta["T"], operand_dtype=torch.float16)
+    assert rel(out["logits"], ref["logits"]) < 3e-3
+    assert (out["logits"].numpy().argmax(1) == ref["logits"].argmax(1)).all()
