@@ -163,21 +163,24 @@ int check_launch(fsar_handle* h, const char* what) {
 }
 
 // ---------------------------------------------------------------- TMA tensor maps
-// Row-major 16-bit matrix [rows, cols] (cols contiguous), box = [box_rows, 64 cols], 128-byte swizzle.
-int get_tmap(fsar_handle* h, const void* ptr, int rows, int cols, int box_rows, CUtensorMap* out) {
-    auto key = std::make_tuple(ptr, rows, cols, box_rows);
+// Row-major matrix [rows, cols] (cols contiguous) of 16-bit operands (f32 == 0) or fp32 (f32 == 1),
+// box = [box_rows, box_cols] with box_cols * elem_size == 128 bytes, 128-byte swizzle.
+int get_tmap(fsar_handle* h, const void* ptr, int rows, int cols, int box_rows, int box_cols, int f32, CUtensorMap* out) {
+    auto key = std::make_tuple(ptr, rows, cols, box_rows * 4 + f32 * 2 + (box_cols == 64 ? 1 : 0));
     auto it = h->tmaps.find(key);
     if (it != h->tmaps.end()) {
         *out = it->second;
         return 0;
     }
-    if ((cols % 8) != 0) return fail(h, FSAR_E_INVALID, "TMA needs a 16-byte row pitch (cols %% 8 == 0), got %d", cols);
+    const int esz = f32 ? 4 : 2;
+    if ((cols * esz) % 16 != 0) return fail(h, FSAR_E_INVALID, "TMA needs a 16-byte row pitch, got %d x %d bytes", cols, esz);
     CUtensorMap m;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-    cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * esz};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUtensorMapDataType dt = kOperandDtype ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : (kOperandDtype ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
     CUresult r = h->encode(&m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -190,8 +193,8 @@ int get_tmap(fsar_handle* h, const void* ptr, int rows, int cols, int box_rows, 
 
 // ---------------------------------------------------------------- GEMM dispatch
 template <int BN, int EPI>
-int launch_gemm_inst(fsar_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                     cudaStream_t st) {
+int launch_gemm_inst(fsar_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                     const GemmParams& p, cudaStream_t st) {
     typedef GemmCfg<BN> Cfg;
     auto kern = gemm_tn_tcgen05_kernel<BN, EPI, T16>;
     static bool attr_done = false;
@@ -202,37 +205,41 @@ int launch_gemm_inst(fsar_handle* h, const CUtensorMap& ta, const CUtensorMap& t
     const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (p.N + BN - 1) / BN;
     const int tiles = m_tiles * n_tiles;
     const int grid = tiles < h->sms ? tiles : h->sms;
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, p);
     return check_launch(h, "gemm_tn_tcgen05_kernel");
 }
 
 template <int BN>
-int launch_gemm_bn(fsar_handle* h, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                   cudaStream_t st) {
+int launch_gemm_bn(fsar_handle* h, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                   const GemmParams& p, cudaStream_t st) {
     switch (epi) {
-        case EPI_STORE16: return launch_gemm_inst<BN, EPI_STORE16>(h, ta, tb, p, st);
-        case EPI_QGELU16: return launch_gemm_inst<BN, EPI_QGELU16>(h, ta, tb, p, st);
-        case EPI_RESID32: return launch_gemm_inst<BN, EPI_RESID32>(h, ta, tb, p, st);
-        case EPI_PATCH32: return launch_gemm_inst<BN, EPI_PATCH32>(h, ta, tb, p, st);
-        case EPI_STORE32: return launch_gemm_inst<BN, EPI_STORE32>(h, ta, tb, p, st);
+        case EPI_STORE16: return launch_gemm_inst<BN, EPI_STORE16>(h, ta, tb, tc, p, st);
+        case EPI_QGELU16: return launch_gemm_inst<BN, EPI_QGELU16>(h, ta, tb, tc, p, st);
+        case EPI_RESID32: return launch_gemm_inst<BN, EPI_RESID32>(h, ta, tb, tc, p, st);
+        case EPI_STORE32: return launch_gemm_inst<BN, EPI_STORE32>(h, ta, tb, tc, p, st);
     }
     return fail(h, FSAR_E_INVALID, "unknown GEMM epilogue %d", epi);
 }
 
-// C[M,N] = A16[M,K] W16[N,K]^T, K = row pitch of both operands.
-int gemm(fsar_handle* h, int cls, const T16* a, const T16* w, int M, int N, int K, int epi, GemmParams p,
+// out[M,N] (epilogue) = A16[M,K] W16[N,K]^T (+ bias); K = row pitch of both operands, N = row pitch of out.
+int gemm(fsar_handle* h, int cls, const T16* a, const T16* w, const float* bias, void* out, int M, int N, int K, int epi,
          cudaStream_t st) {
     if (M <= 0 || N <= 0 || K <= 0 || (N % 8) != 0 || (K % 8) != 0)
         return fail(h, FSAR_E_INVALID, "gemm: unsupported shape M=%d N=%d K=%d (need N %% 8 == 0, K %% 8 == 0)", M, N, K);
-    p.M = M; p.N = N; p.K = K;
+    if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out)) & 15)
+        return fail(h, FSAR_E_INVALID, "gemm: operands must be 16-byte aligned");
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K; p.bias = bias;
     const int bn = (N >= 256) ? 256 : ((N >= 128) ? 128 : 64);
-    CUtensorMap ta, tb;
-    RET_IF(get_tmap(h, a, M, K, GEMM_BM, &ta));
-    RET_IF(get_tmap(h, w, N, K, bn, &tb));
+    const bool out16 = (epi == EPI_STORE16 || epi == EPI_QGELU16);
+    CUtensorMap ta, tb, tc;
+    RET_IF(get_tmap(h, a, M, K, GEMM_BM, GEMM_BK, 0, &ta));
+    RET_IF(get_tmap(h, w, N, K, bn, GEMM_BK, 0, &tb));
+    RET_IF(get_tmap(h, out, M, N, 32, out16 ? 64 : 32, out16 ? 0 : 1, &tc));
     Scope s(h, st, cls, 2.0 * M * N * K, 0.0);
-    if (bn == 256) return launch_gemm_bn<256>(h, epi, ta, tb, p, st);
-    if (bn == 128) return launch_gemm_bn<128>(h, epi, ta, tb, p, st);
-    return launch_gemm_bn<64>(h, epi, ta, tb, p, st);
+    if (bn == 256) return launch_gemm_bn<256>(h, epi, ta, tb, tc, p, st);
+    if (bn == 128) return launch_gemm_bn<128>(h, epi, ta, tb, tc, p, st);
+    return launch_gemm_bn<64>(h, epi, ta, tb, tc, p, st);
 }
 
 // ---------------------------------------------------------------- small launch wrappers
@@ -258,13 +265,13 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, T16* __restric
 }
 
 int layernorm(fsar_handle* h, const float* x, void* out, const float* g, const float* b, int rows, int D, bool out16,
-              bool cls_fill, int tokens, const float* cls_emb, const float* pos0, cudaStream_t st, int cls) {
+              bool embed, int tokens, const float* cls_emb, const float* pos, cudaStream_t st, int cls) {
     if ((D % 128) != 0 || D > 1024) return fail(h, FSAR_E_INVALID, "layernorm: dim %d must be a multiple of 128 and <= 1024", D);
     const int wpb = 8;
     const int grid = (rows + wpb - 1) / wpb;
     Scope s(h, st, cls, 0.0, (double)rows * D * (4.0 + (out16 ? 2.0 : 4.0)));
-    if (cls_fill)
-        layernorm_kernel<T16, false, true><<<grid, 256, 0, st>>>(x, out, g, b, rows, D, 1e-5f, tokens, cls_emb, pos0);
+    if (embed)
+        layernorm_kernel<T16, false, true><<<grid, 256, 0, st>>>(x, out, g, b, rows, D, 1e-5f, tokens, cls_emb, pos);
     else if (out16)
         layernorm_kernel<T16, true, false><<<grid, 256, 0, st>>>(x, out, g, b, rows, D, 1e-5f, tokens, nullptr, nullptr);
     else
@@ -305,7 +312,8 @@ int linear_f32(fsar_handle* h, const float* A, const float* W, const float* bias
                int N, int K, cudaStream_t st) {
     const dim3 grid((N + LIN_BN - 1) / LIN_BN, (R + LIN_BM - 1) / LIN_BM);
     Scope s(h, st, FSAR_K_MODULATOR, 2.0 * R * N * K, 4.0 * ((double)N * K + (double)R * K + (double)R * N));
-    linear_f32_kernel<ACT><<<grid, 256, 0, st>>>(A, W, bias, residual, C, R, N, K);
+    if ((K % LIN_BK) != 0) return fail(h, FSAR_E_INVALID, "linear: K=%d must be a multiple of %d", K, LIN_BK);
+    linear_f32_kernel<ACT><<<grid, LIN_THREADS, 0, st>>>(A, W, bias, residual, C, R, N, K);
     return check_launch(h, "linear_f32_kernel");
 }
 
@@ -442,36 +450,32 @@ int vit_encode_gathered(fsar_handle* h, int n, float* feats_out, cudaStream_t st
     const fsar_config& c = h->cfg;
     const int D = c.width, L = h->tokens, G2 = h->grid * h->grid;
     const int M = n * L;
-    {   // conv1 as a GEMM; the epilogue adds the positional embedding and scatters to token rows 1..G*G
-        GemmParams p{};
-        p.bias = nullptr; p.out = h->x32; p.ldo = D;
-        p.pos = W32(h, "backbone.positional_embedding"); p.patches_per_frame = G2;
-        RET_IF(gemm(h, FSAR_K_GEMM_PATCH, h->patches16, W16(h, "backbone.conv1.weight"), n * G2, D, h->patch_kp,
-                    EPI_PATCH32, p, st));
-    }
-    // ln_pre in place; CLS rows take class_embedding + positional_embedding[0] as their input
-    RET_IF(layernorm(h, h->x32, h->x32, W32(h, "backbone.ln_pre.weight"), W32(h, "backbone.ln_pre.bias"), M, D, false,
+    // conv1 as a GEMM into a scratch [n * G * G, D] fp32 (the MLP hidden buffer is free at this point) ...
+    float* patch32 = reinterpret_cast<float*>(h->h16);
+    RET_IF(gemm(h, FSAR_K_GEMM_PATCH, h->patches16, W16(h, "backbone.conv1.weight"), nullptr, patch32, n * G2, D,
+                h->patch_kp, EPI_STORE32, st));
+    // ... and ln_pre assembles [CLS | patches] + positional embedding on the fly (few_shot.py:675-677)
+    RET_IF(layernorm(h, patch32, h->x32, W32(h, "backbone.ln_pre.weight"), W32(h, "backbone.ln_pre.bias"), M, D, false,
                      true, L, W32(h, "backbone.class_embedding"), W32(h, "backbone.positional_embedding"), st,
                      FSAR_K_LAYERNORM));
     for (int i = 0; i < c.layers; ++i) {
         const std::string pre = "backbone.transformer.resblocks." + std::to_string(i) + ".";
         RET_IF(layernorm(h, h->x32, h->ln16, W32(h, pre + "ln_1.weight"), W32(h, pre + "ln_1.bias"), M, D, true, false, L,
                          nullptr, nullptr, st, FSAR_K_LAYERNORM));
-        GemmParams p{};
-        p.bias = W32(h, pre + "attn.in_proj_bias"); p.out = h->qkv16; p.ldo = 3 * D;
-        RET_IF(gemm(h, FSAR_K_GEMM_QKV, h->ln16, W16(h, pre + "attn.in_proj_weight"), M, 3 * D, D, EPI_STORE16, p, st));
+        RET_IF(gemm(h, FSAR_K_GEMM_QKV, h->ln16, W16(h, pre + "attn.in_proj_weight"), W32(h, pre + "attn.in_proj_bias"),
+                    h->qkv16, M, 3 * D, D, EPI_STORE16, st));
         RET_IF(attention(h, h->qkv16, n, L, c.heads, h->att16, st));
-        p.bias = W32(h, pre + "attn.out_proj.bias"); p.out = h->x32; p.ldo = D;
-        RET_IF(gemm(h, FSAR_K_GEMM_OUT, h->att16, W16(h, pre + "attn.out_proj.weight"), M, D, D, EPI_RESID32, p, st));
+        RET_IF(gemm(h, FSAR_K_GEMM_OUT, h->att16, W16(h, pre + "attn.out_proj.weight"), W32(h, pre + "attn.out_proj.bias"),
+                    h->x32, M, D, D, EPI_RESID32, st));
         RET_IF(layernorm(h, h->x32, h->ln16, W32(h, pre + "ln_2.weight"), W32(h, pre + "ln_2.bias"), M, D, true, false, L,
                          nullptr, nullptr, st, FSAR_K_LAYERNORM));
-        p.bias = W32(h, pre + "mlp.c_fc.bias"); p.out = h->h16; p.ldo = 4 * D;
-        RET_IF(gemm(h, FSAR_K_GEMM_FC1, h->ln16, W16(h, pre + "mlp.c_fc.weight"), M, 4 * D, D, EPI_QGELU16, p, st));
-        p.bias = W32(h, pre + "mlp.c_proj.bias"); p.out = h->x32; p.ldo = D;
-        RET_IF(gemm(h, FSAR_K_GEMM_FC2, h->h16, W16(h, pre + "mlp.c_proj.weight"), M, D, 4 * D, EPI_RESID32, p, st));
+        RET_IF(gemm(h, FSAR_K_GEMM_FC1, h->ln16, W16(h, pre + "mlp.c_fc.weight"), W32(h, pre + "mlp.c_fc.bias"), h->h16, M,
+                    4 * D, D, EPI_QGELU16, st));
+        RET_IF(gemm(h, FSAR_K_GEMM_FC2, h->h16, W16(h, pre + "mlp.c_proj.weight"), W32(h, pre + "mlp.c_proj.bias"), h->x32,
+                    M, D, 4 * D, EPI_RESID32, st));
     }
     {
-        const int grid = (n + FINAL_FPC - 1) / FINAL_FPC;
+        const dim3 grid((n + FINAL_FPC - 1) / FINAL_FPC, (c.embed_dim + FINAL_COLS - 1) / FINAL_COLS);
         Scope s(h, st, FSAR_K_FINAL_PROJ, 2.0 * n * D * c.embed_dim, 4.0 * ((double)D * c.embed_dim + (double)n * D));
         final_proj_kernel<<<grid, 256, sizeof(float) * FINAL_FPC * D, st>>>(
             h->x32, W32(h, "backbone.ln_post.weight"), W32(h, "backbone.ln_post.bias"), W32(h, "backbone.proj"),
@@ -891,10 +895,8 @@ int fsar_op_layernorm(fsar_handle* h, const float* x_dev, const float* gamma_dev
 int fsar_op_gemm(fsar_handle* h, const void* a16_dev, const void* w16_dev, const float* bias_dev, int M, int N, int K, int epi,
                  void* out_dev, void* stream) {
     if (h == nullptr || a16_dev == nullptr || w16_dev == nullptr || out_dev == nullptr) return fail(h, FSAR_E_INVALID, "fsar_op_gemm: NULL argument");
-    if (epi == EPI_PATCH32) return fail(h, FSAR_E_INVALID, "fsar_op_gemm: the patch epilogue is internal");
-    GemmParams p{};
-    p.bias = bias_dev; p.out = out_dev; p.ldo = N;
-    return gemm(h, FSAR_K_GEMM_QKV, (const T16*)a16_dev, (const T16*)w16_dev, M, N, K, epi, p, (cudaStream_t)stream);
+    return gemm(h, FSAR_K_GEMM_QKV, (const T16*)a16_dev, (const T16*)w16_dev, bias_dev, out_dev, M, N, K, epi,
+                (cudaStream_t)stream);
 }
 
 int fsar_op_attention(fsar_handle* h, const void* qkv16_dev, int n_frames, int L, int heads, void* out16_dev, void* stream) {

@@ -8,35 +8,38 @@
 //   EPI_STORE16 : out16 = acc + bias                      (QKV projection)
 //   EPI_QGELU16 : out16 = quick_gelu(acc + bias)          (c_fc + QuickGELU, few_shot.py:616)
 //   EPI_RESID32 : x32  += acc + bias                      (attn out-proj / c_proj + residual, :638-639)
-//   EPI_PATCH32 : x32[frame, 1 + patch] = acc + pos[1 + patch]   (conv1 + positional embedding, :672-676)
-//   EPI_STORE32 : out32 = acc + bias                      (generic, used by the self tests)
+//   EPI_STORE32 : out32 = acc + bias                      (conv1 patch GEMM, generic)
 //
-// Structure (one CTA per SM, 256 threads):
+// Structure (one CTA per SM, 384 threads):
 //   warp 0   TMA producer  : cp.async.bulk.tensor 2D tiles (128B swizzle) into a STAGES-deep smem ring
 //   warp 1   MMA issuer    : one lane issues tcgen05.mma 128 x BN x 16, accumulators double-buffered in TMEM
 //   warp 2   TMEM allocator
-//   warps 4-7 epilogue     : tcgen05.ld 32 lanes x 32 columns -> registers -> fused tail -> global
-// Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue).
+//   warps 4-11 epilogue    : two warps per TMEM lane quarter (alternating column chunks, so every SM sub-partition
+//                            has two epilogue warps to hide MUFU / TMEM-load latency behind each other):
+//                            tcgen05.ld (32 lanes x 32 columns) -> registers -> fused tail -> 128B-swizzled smem
+//                            staging tile -> TMA store (or TMA reduce-add for the fp32 residual: x += tile is done
+//                            in L2, the SM never reads the residual stream)
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue),
+//            bulk async-groups (one epilogue staging buffer per warp).
 #pragma once
 #include <type_traits>
 #include "ptx.cuh"
 
 namespace fsar {
 
-enum GemmEpilogue : int { EPI_STORE16 = 0, EPI_QGELU16 = 1, EPI_RESID32 = 2, EPI_PATCH32 = 3, EPI_STORE32 = 4 };
+enum GemmEpilogue : int { EPI_STORE16 = 0, EPI_QGELU16 = 1, EPI_RESID32 = 2, EPI_STORE32 = 4 };
 
 struct GemmParams {
-    int M, N, K;            // logical sizes; K is covered in blocks of 64 (TMA zero-fills the tail)
-    const float* bias;      // [N] or nullptr
-    void* out;              // fp16/bf16 [M, ldo] or fp32 [*, ldo]
-    int ldo;                // row pitch of out in elements
-    const float* pos;       // EPI_PATCH32: positional embedding [(P + 1), N]
-    int patches_per_frame;  // EPI_PATCH32: P (196 for 224/16)
+    int M, N, K;        // logical sizes; K is covered in blocks of 64 (TMA zero-fills the tail)
+    const float* bias;  // [N] or nullptr
 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 x 2 B = 128 B = one swizzle-128B row
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 128 + 32 * GEMM_EPI_WARPS;
+constexpr int GEMM_STAGE_TILE_BYTES = 32 * 128;  // epilogue staging tile: 32 rows x 128 B
+constexpr int GEMM_STAGING_BYTES = GEMM_EPI_WARPS * GEMM_STAGE_TILE_BYTES;  // one buffer per epilogue warp
 
 template <int BN>
 struct GemmCfg {
@@ -46,7 +49,7 @@ struct GemmCfg {
     static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : ((2 * BN <= 64) ? 64 : ((2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512)));
     static constexpr int BAR_BYTES = 256;  // barriers + tmem pointer
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 for manual 1 KB alignment
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_STAGING_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
 };
 
 template <typename T>
@@ -63,24 +66,28 @@ __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
 }
 
 __device__ __forceinline__ float quick_gelu(float v) {
-    // x * sigmoid(1.702 x), few_shot.py:616
-    return v / (1.0f + __expf(-1.702f * v));
+    // x * sigmoid(1.702 x), few_shot.py:616.  ex2.approx + rcp.approx (2 ulp each): far below the 16-bit output rounding
+    return __fdividef(v, 1.0f + __expf(-1.702f * v));
 }
 
 template <int BN, int EPI, typename T16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const GemmParams p) {
+                       const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr bool kBf16 = std::is_same<T16, __nv_bfloat16>::value;
+    constexpr bool kOut16 = (EPI == EPI_STORE16 || EPI == EPI_QGELU16);
+    constexpr int CHUNK = kOut16 ? 64 : 32;  // output columns per staging tile (128 B per row)
+    static_assert(BN % CHUNK == 0, "tile width must be a multiple of the staging chunk");
 
     extern __shared__ uint8_t smem_raw[];
     // swizzle-128B tiles need 1024 B alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;                                // STAGES x [128][64] 16-bit
     uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;        // STAGES x [BN][64] 16-bit
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint8_t* smem_stage = smem + STAGES * Cfg::STAGE_BYTES;  // 8 warps x [32 rows][128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + GEMM_STAGING_BYTES);
     uint64_t* full_bar = bars;                 // [STAGES]
     uint64_t* empty_bar = bars + STAGES;       // [STAGES]
     uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
@@ -98,6 +105,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -106,7 +114,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+            mbar_init(&tempty_bar[i], GEMM_EPI_WARPS);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -125,8 +133,9 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / n_tiles;
-                const int n_blk = tile - m_blk * n_tiles;
+                // n-major tile order: the CTAs of one wave share few weight tiles and stream distinct A tiles
+                const int n_blk = tile / m_tiles;
+                const int m_blk = tile - n_blk * m_tiles;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -179,98 +188,105 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------ epilogue
-        const int q = warp - 4;  // TMEM lane quarter this warp may access (== warp % 4)
+        const int q = warp & 3;          // TMEM lane quarter this warp may access (== warp % 4)
+        const int half = (warp - 4) >> 2;  // which of the two warps of this quarter: even or odd column chunks
+        uint8_t* stage_ptr = smem_stage + (warp - 4) * GEMM_STAGE_TILE_BYTES;
+        const uint32_t row_addr = smem_u32(stage_ptr) + lane * 128;  // this thread's row inside the staging tile
+        const uint32_t sw = uint32_t(lane & 7);                      // 128B swizzle: 16-byte chunk index ^= row % 8
+        constexpr int NCH = BN / CHUNK;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile / n_tiles;
-            const int n_blk = tile - m_blk * n_tiles;
-            const int row = m_blk * GEMM_BM + q * 32 + lane;
-            const bool row_ok = row < p.M;
+            const int n_blk = tile / m_tiles;
+            const int m_blk = tile - n_blk * m_tiles;
+            const int row0 = m_blk * GEMM_BM + q * 32;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_base = tmem_base + acc * BN + (uint32_t(q * 32) << 16);
-
-            size_t out_row_off;
-            const float* pos_row = nullptr;
-            if (EPI == EPI_PATCH32) {
-                const int frame = row / p.patches_per_frame;
-                const int patch = row - frame * p.patches_per_frame;
-                out_row_off = (size_t(frame) * (p.patches_per_frame + 1) + 1 + patch) * size_t(p.ldo);
-                pos_row = p.pos + size_t(1 + patch) * p.N;
-            } else {
-                out_row_off = size_t(row) * size_t(p.ldo);
-            }
+            bool released = false;
 
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                const int col0 = n_blk * BN + c * 32;
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(t_base + c * 32, r);
-                tc_wait_ld();
-                if (row_ok && col0 < p.N) {
-                    float v[32];
+            for (int c = half; c < NCH; c += 2) {
+                const int col0 = n_blk * BN + c * CHUNK;
+                uint32_t w[32];  // the staging row of this thread: 128 B
+                if (kOut16) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld_32x32b_x32(t_base + c * 64, r0);
+                    tmem_ld_32x32b_x32(t_base + c * 64 + 32, r1);
+                    tc_wait_ld();
+                    if (c + 2 >= NCH) {  // this warp's share of the accumulator is read: hand it back early
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                        released = true;
+                    }
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                        if (p.bias != nullptr) {
+                            if (col0 + j < p.N) b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                            if (col0 + 32 + j < p.N) b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 32 + j));
+                        }
+                        float v0 = __uint_as_float(r0[j]) + b0.x, v1 = __uint_as_float(r0[j + 1]) + b0.y;
+                        float v2 = __uint_as_float(r0[j + 2]) + b0.z, v3 = __uint_as_float(r0[j + 3]) + b0.w;
+                        float u0 = __uint_as_float(r1[j]) + b1.x, u1 = __uint_as_float(r1[j + 1]) + b1.y;
+                        float u2 = __uint_as_float(r1[j + 2]) + b1.z, u3 = __uint_as_float(r1[j + 3]) + b1.w;
+                        if (EPI == EPI_QGELU16) {
+                            v0 = quick_gelu(v0); v1 = quick_gelu(v1); v2 = quick_gelu(v2); v3 = quick_gelu(v3);
+                            u0 = quick_gelu(u0); u1 = quick_gelu(u1); u2 = quick_gelu(u2); u3 = quick_gelu(u3);
+                        }
+                        w[j / 2] = pack2<T16>(v0, v1);
+                        w[j / 2 + 1] = pack2<T16>(v2, v3);
+                        w[16 + j / 2] = pack2<T16>(u0, u1);
+                        w[16 + j / 2 + 1] = pack2<T16>(u2, u3);
+                    }
+                } else {
+                    tmem_ld_32x32b_x32(t_base + c * 32, w);
+                    tc_wait_ld();
+                    if (c + 2 >= NCH) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                        released = true;
+                    }
                     if (p.bias != nullptr) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            if (col0 + j < p.N) {  // N % 8 == 0 is enforced on the host
+                            if (col0 + j < p.N) {
                                 const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                                w[j] = __float_as_uint(__uint_as_float(w[j]) + b.x);
+                                w[j + 1] = __float_as_uint(__uint_as_float(w[j + 1]) + b.y);
+                                w[j + 2] = __float_as_uint(__uint_as_float(w[j + 2]) + b.z);
+                                w[j + 3] = __float_as_uint(__uint_as_float(w[j + 3]) + b.w);
                             }
-                        }
-                    }
-                    if (EPI == EPI_STORE16 || EPI == EPI_QGELU16) {
-                        if (EPI == EPI_QGELU16) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
-                        }
-                        T16* o = reinterpret_cast<T16*>(p.out) + out_row_off + col0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint4 w;
-                            w.x = pack2<T16>(v[j], v[j + 1]);
-                            w.y = pack2<T16>(v[j + 2], v[j + 3]);
-                            w.z = pack2<T16>(v[j + 4], v[j + 5]);
-                            w.w = pack2<T16>(v[j + 6], v[j + 7]);
-                            if (col0 + j < p.N) *reinterpret_cast<uint4*>(o + j) = w;
-                        }
-                    } else {
-                        float* o = reinterpret_cast<float*>(p.out) + out_row_off + col0;
-                        if (EPI == EPI_RESID32) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                if (col0 + j < p.N) {
-                                    const float4 x = *reinterpret_cast<const float4*>(o + j);
-                                    v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
-                                }
-                            }
-                        } else if (EPI == EPI_PATCH32) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                if (col0 + j < p.N) {
-                                    const float4 x = __ldg(reinterpret_cast<const float4*>(pos_row + col0 + j));
-                                    v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            if (col0 + j < p.N)
-                                *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                         }
                     }
                 }
+                // the staging buffer must have been drained by the previous TMA store of this warp
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    st_shared_v4(row_addr + ((uint32_t(j) ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0 && row0 < p.M && col0 < p.N) {
+                    if (EPI == EPI_RESID32) tma_reduce_add_2d(&tmC, stage_ptr, col0, row0);
+                    else tma_store_2d(&tmC, stage_ptr, col0, row0);
+                    tma_store_commit();
+                }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (!released) {  // no chunk for this warp in such a narrow tile: still release the accumulator
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            }
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;
             }
         }
+        if (lane == 0) tma_store_wait<0>();  // all output tiles are globally written before the CTA retires
     }
 
     tc_fence_before();

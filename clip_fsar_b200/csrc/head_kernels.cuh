@@ -120,53 +120,73 @@ build_sequences_kernel(const float* __restrict__ sup, const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// fp32 linear layer  C[R, N] = A[R, K] * W[N, K]^T (+ bias) (GELU) (+ residual).  SIMT, fp32 FMA:
-// the modulator is 3.1 M parameters and bound by reading them once; fp32 keeps parity with the
-// reference at ~1e-6. Tile 32 x 64, BK 32, 256 threads, 2 x 4 outputs per thread.
+// fp32 linear layer  C[R, N] = A[R, K] * W[N, K]^T (+ bias) (GELU) (+ residual).  SIMT fp32 FMA: the modulator is
+// 3.1 M parameters / 0.5 GFLOP per episode, i.e. bound by launch latency and by how many SMs stream the weights,
+// not by math; fp32 keeps parity with the reference at ~1e-6. Small tiles (16 rows x 32 columns, 64 threads) so
+// that even R = 85, N = 512 spreads over ~100 CTAs; global -> register prefetch of the next K-slab overlaps the
+// FMAs of the current one. K % 32 == 0 (512 / 2048 / 768 here).
 enum LinAct : int { LIN_NONE = 0, LIN_GELU = 1 };
-constexpr int LIN_BM = 32, LIN_BN = 64, LIN_BK = 32;
+constexpr int LIN_BM = 16, LIN_BN = 32, LIN_BK = 32, LIN_THREADS = 64;
 
 template <int ACT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(LIN_THREADS)
 linear_f32_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
                   const float* residual, float* C, int R, int N, int K) {
-    __shared__ float sA[LIN_BK][LIN_BM + 1];
-    __shared__ float sW[LIN_BK][LIN_BN + 1];
+    __shared__ float sA[LIN_BK][LIN_BM + 1];   // [k][row]
+    __shared__ __align__(16) float sW[LIN_BK][LIN_BN + 4];   // [k][col], 16-byte aligned rows for float4 reads
     const int r0 = blockIdx.y * LIN_BM, n0 = blockIdx.x * LIN_BN;
     const int tid = threadIdx.x;
-    const int tr = tid >> 4;   // 0..15 -> rows tr*2, tr*2+1
-    const int tc = tid & 15;   // 0..15 -> cols tc + 16*j
-    float acc[2][4] = {};
-    for (int k0 = 0; k0 < K; k0 += LIN_BK) {
-        // A tile: 32 rows x 32 k
-        for (int i = tid; i < LIN_BM * LIN_BK; i += 256) {
-            const int r = i / LIN_BK, k = i - r * LIN_BK;
-            sA[k][r] = (r0 + r < R && k0 + k < K) ? A[(size_t)(r0 + r) * K + k0 + k] : 0.f;
+    const int ty = tid >> 3;   // 0..7  -> rows ty * 2, ty * 2 + 1
+    const int tx = tid & 7;    // 0..7  -> cols tx * 4 .. tx * 4 + 3
+    // loader mapping: a float4 along K per thread; A tile = 16 rows x 8 float4 = 128 -> 2 per thread,
+    //                                               W tile = 32 rows x 8 float4 = 256 -> 4 per thread
+    const int lrow = tid >> 3, lk = (tid & 7) * 4;
+    float4 ra[2], rw[4];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = r0 + lrow + 8 * i;
+            ra[i] = (r < R) ? *reinterpret_cast<const float4*>(A + (size_t)r * K + k0 + lk) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        for (int i = tid; i < LIN_BN * LIN_BK; i += 256) {
-            const int n = i / LIN_BK, k = i - n * LIN_BK;
-            sW[k][n] = (n0 + n < N && k0 + k < K) ? __ldg(W + (size_t)(n0 + n) * K + k0 + k) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int n = n0 + lrow + 8 * i;
+            rw[i] = (n < N) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)n * K + k0 + lk)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    float acc[2][4] = {};
+    fetch(0);
+    for (int k0 = 0; k0 < K; k0 += LIN_BK) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = lrow + 8 * i;
+            sA[lk][r] = ra[i].x; sA[lk + 1][r] = ra[i].y; sA[lk + 2][r] = ra[i].z; sA[lk + 3][r] = ra[i].w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int n = lrow + 8 * i;
+            sW[lk][n] = rw[i].x; sW[lk + 1][n] = rw[i].y; sW[lk + 2][n] = rw[i].z; sW[lk + 3][n] = rw[i].w;
         }
         __syncthreads();
+        if (k0 + LIN_BK < K) fetch(k0 + LIN_BK);   // in flight while we compute
 #pragma unroll
         for (int k = 0; k < LIN_BK; ++k) {
-            const float a0 = sA[k][tr * 2], a1 = sA[k][tr * 2 + 1];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float w = sW[k][tc + 16 * j];
-                acc[0][j] = fmaf(a0, w, acc[0][j]);
-                acc[1][j] = fmaf(a1, w, acc[1][j]);
-            }
+            const float a0 = sA[k][ty * 2], a1 = sA[k][ty * 2 + 1];
+            const float4 w = *reinterpret_cast<const float4*>(&sW[k][tx * 4]);
+            acc[0][0] = fmaf(a0, w.x, acc[0][0]); acc[0][1] = fmaf(a0, w.y, acc[0][1]);
+            acc[0][2] = fmaf(a0, w.z, acc[0][2]); acc[0][3] = fmaf(a0, w.w, acc[0][3]);
+            acc[1][0] = fmaf(a1, w.x, acc[1][0]); acc[1][1] = fmaf(a1, w.y, acc[1][1]);
+            acc[1][2] = fmaf(a1, w.z, acc[1][2]); acc[1][3] = fmaf(a1, w.w, acc[1][3]);
         }
         __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-        const int r = r0 + tr * 2 + i;
+        const int r = r0 + ty * 2 + i;
         if (r >= R) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tc + 16 * j;
+            const int n = n0 + tx * 4 + j;
             if (n >= N) continue;
             float v = acc[i][j];
             if (bias != nullptr) v += bias[n];

@@ -52,29 +52,37 @@ __global__ void patch_gather_kernel(const float* __restrict__ frames, T16* __res
 // ------------------------------------------------------------------------------------------------
 // LayerNorm over the last dimension, one warp per row, statistics in fp32 (two-pass in registers).
 //   D % 128 == 0, D <= 1024.  OUT16: write T16, else write fp32 (may alias the input: in-place).
-//   CLS_FILL: rows whose token index (row % tokens) is 0 take class_embedding + positional_embedding[0]
-//   as their input instead of x (few_shot.py:675-677); other rows already hold conv1 + pos (GEMM epilogue).
-template <typename T16, bool OUT16, bool CLS_FILL>
+//   EMBED (ln_pre, few_shot.py:675-677): the input row of (frame f, token t) is assembled on the fly as
+//     t == 0 : class_embedding + positional_embedding[0]
+//     t >= 1 : patch_out[f * (tokens - 1) + t - 1] + positional_embedding[t]     (patch_out = conv1 GEMM output)
+//   so the concatenated / position-embedded sequence is never materialised before the LayerNorm.
+template <typename T16, bool OUT16, bool EMBED>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x, void* out, const float* __restrict__ gamma, const float* __restrict__ beta,
                  int rows, int D, float eps, int tokens, const float* __restrict__ cls_emb,
-                 const float* __restrict__ pos0) {
+                 const float* __restrict__ pos) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + warp;
     if (row >= rows) return;
     const int nv = D >> 7;  // float4 per lane
     float4 v[8];
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
-    const bool is_cls = CLS_FILL && (row % tokens == 0);
+    const float4* pr = nullptr;
+    bool is_cls = false;
+    if (EMBED) {
+        const int f = row / tokens, t = row - f * tokens;
+        is_cls = (t == 0);
+        pr = reinterpret_cast<const float4*>(pos + (size_t)t * D);
+        xr = is_cls ? reinterpret_cast<const float4*>(cls_emb)
+                    : reinterpret_cast<const float4*>(x + ((size_t)f * (tokens - 1) + (t - 1)) * D);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         if (i < nv) {
-            if (is_cls) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(cls_emb) + lane + 32 * i);
-                const float4 b = __ldg(reinterpret_cast<const float4*>(pos0) + lane + 32 * i);
-                v[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-            } else {
-                v[i] = xr[lane + 32 * i];
+            v[i] = xr[lane + 32 * i];
+            if (EMBED) {
+                const float4 b = __ldg(pr + lane + 32 * i);
+                v[i].x += b.x; v[i].y += b.y; v[i].z += b.z; v[i].w += b.w;
             }
         }
     }
@@ -118,8 +126,10 @@ layernorm_kernel(const float* x, void* out, const float* __restrict__ gamma, con
 }
 
 // ------------------------------------------------------------------------------------------------
-// ln_post(x[:, 0, :]) @ proj  (few_shot.py:683-686). One CTA handles FPC frames; proj is [D, E] fp32.
+// ln_post(x[:, 0, :]) @ proj  (few_shot.py:683-686). proj is [D, E] fp32.
+// grid = (ceil(frames / FPC), E / FINAL_COLS); 256 threads = FINAL_COLS columns x 2 halves of the D reduction.
 constexpr int FINAL_FPC = 4;
+constexpr int FINAL_COLS = 128;
 __global__ void __launch_bounds__(256)
 final_proj_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                   const float* __restrict__ proj, float* __restrict__ out, int n_frames, int tokens, int D, int E,
@@ -168,18 +178,31 @@ final_proj_kernel(const float* __restrict__ x, const float* __restrict__ gamma, 
         for (int d = threadIdx.x; d < D; d += blockDim.x)
             sm[f * D + d] = (sm[f * D + d] - mean[f]) * rstd[f] * gamma[d] + beta[d];
     __syncthreads();
-    for (int e = threadIdx.x; e < E; e += blockDim.x) {
-        float acc[FINAL_FPC];
+    // projection: column e of this CTA's slice, half `kh` of the D reduction; halves are combined through smem
+    __shared__ float part[FINAL_FPC][FINAL_COLS];
+    const int e = blockIdx.y * FINAL_COLS + (threadIdx.x & (FINAL_COLS - 1));
+    const int kh = threadIdx.x / FINAL_COLS;  // 0 or 1
+    const int dlo = kh * (D >> 1), dhi = dlo + (D >> 1);
+    float acc[FINAL_FPC];
 #pragma unroll
-        for (int f = 0; f < FINAL_FPC; ++f) acc[f] = 0.f;
-        for (int d = 0; d < D; ++d) {
+    for (int f = 0; f < FINAL_FPC; ++f) acc[f] = 0.f;
+    if (e < E) {
+#pragma unroll 4
+        for (int d = dlo; d < dhi; ++d) {
             const float w = __ldg(proj + (size_t)d * E + e);
 #pragma unroll
             for (int f = 0; f < FINAL_FPC; ++f) acc[f] = fmaf(sm[f * D + d], w, acc[f]);
         }
+    }
+    if (kh == 1) {
+#pragma unroll
+        for (int f = 0; f < FINAL_FPC; ++f) part[f][threadIdx.x & (FINAL_COLS - 1)] = acc[f];
+    }
+    __syncthreads();
+    if (kh == 0 && e < E) {
 #pragma unroll
         for (int f = 0; f < FINAL_FPC; ++f)
-            if (f0 + f < n_frames) out[(size_t)(f0 + f) * E + e] = acc[f];
+            if (f0 + f < n_frames) out[(size_t)(f0 + f) * E + e] = acc[f] + part[f][threadIdx.x];
     }
 }
 

@@ -146,7 +146,7 @@ int64_t fsar_peek(fsar_handle* h, const char* name, void* dst_host, int64_t nume
 int fsar_operand_dtype(void);
 int fsar_op_layernorm(fsar_handle* h, const float* x_dev, const float* gamma_dev, const float* beta_dev, int rows,
                       int dim, int out16, void* out_dev, void* stream);
-/* C[M,N] = A16[M,K] * W16[N,K]^T with epilogue epi (0 store16, 1 quickgelu16, 2 resid32 (+=), 4 store32). */
+/* C[M,N] = A16[M,K] * W16[N,K]^T with epilogue epi (0 store16, 1 quickgelu16, 2 resid32 (out += ...), 4 store32). */
 int fsar_op_gemm(fsar_handle* h, const void* a16_dev, const void* w16_dev, const float* bias_dev, int M, int N, int K,
                  int epi, void* out_dev, void* stream);
 /* qkv16 [n_frames * L, 3 * D] -> out16 [n_frames * L, D], D = heads * 64 */
