@@ -312,7 +312,7 @@ int linear_f32(fsar_handle* h, const float* A, const float* W, const float* bias
                int N, int K, cudaStream_t st) {
     const dim3 grid((N + LIN_BN - 1) / LIN_BN, (R + LIN_BM - 1) / LIN_BM);
     Scope s(h, st, FSAR_K_MODULATOR, 2.0 * R * N * K, 4.0 * ((double)N * K + (double)R * K + (double)R * N));
-    if ((K % LIN_BK) != 0) return fail(h, FSAR_E_INVALID, "linear: K=%d must be a multiple of %d", K, LIN_BK);
+    if ((K % (LIN_BK * LIN_WARPS)) != 0) return fail(h, FSAR_E_INVALID, "linear: K=%d must be a multiple of %d", K, LIN_BK * LIN_WARPS);
     linear_f32_kernel<ACT><<<grid, LIN_THREADS, 0, st>>>(A, W, bias, residual, C, R, N, K);
     return check_launch(h, "linear_f32_kernel");
 }

@@ -121,79 +121,102 @@ build_sequences_kernel(const float* __restrict__ sup, const float* __restrict__ 
 
 // ------------------------------------------------------------------------------------------------
 // fp32 linear layer  C[R, N] = A[R, K] * W[N, K]^T (+ bias) (GELU) (+ residual).  SIMT fp32 FMA: the modulator is
-// 3.1 M parameters / 0.5 GFLOP per episode, i.e. bound by launch latency and by how many SMs stream the weights,
-// not by math; fp32 keeps parity with the reference at ~1e-6. Small tiles (16 rows x 32 columns, 64 threads) so
-// that even R = 85, N = 512 spreads over ~100 CTAs; global -> register prefetch of the next K-slab overlaps the
-// FMAs of the current one. K % 32 == 0 (512 / 2048 / 768 here).
+// 3.1 M parameters / 0.5 GFLOP per episode, i.e. bound by latency and by how many SMs stream the weights, not by
+// math; fp32 keeps parity with the reference at ~1e-6.
+// CTA tile 16 rows x 32 columns; the K dimension is split over the CTA's 4 warps (each warp owns K/4 and private
+// smem slabs, so the main loop has no block-wide barrier and 12 float4 loads per lane are in flight while the
+// previous slab is being multiplied); the four partial tiles are summed through smem in a fixed order
+// (deterministic). K % 128 == 0 (512 / 2048 / 768 / 128 / 256 here).
 enum LinAct : int { LIN_NONE = 0, LIN_GELU = 1 };
-constexpr int LIN_BM = 16, LIN_BN = 32, LIN_BK = 32, LIN_THREADS = 64;
+constexpr int LIN_BM = 16, LIN_BN = 32, LIN_BK = 32, LIN_WARPS = 4, LIN_THREADS = 32 * LIN_WARPS;
 
 template <int ACT>
 __global__ void __launch_bounds__(LIN_THREADS)
 linear_f32_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
                   const float* residual, float* C, int R, int N, int K) {
-    __shared__ float sA[LIN_BK][LIN_BM + 1];   // [k][row]
-    __shared__ __align__(16) float sW[LIN_BK][LIN_BN + 4];   // [k][col], 16-byte aligned rows for float4 reads
+    __shared__ __align__(16) float sA[LIN_WARPS][LIN_BK][LIN_BM + 4];   // [warp][k][row]
+    __shared__ __align__(16) float sW[LIN_WARPS][LIN_BK][LIN_BN + 4];   // [warp][k][col]
     const int r0 = blockIdx.y * LIN_BM, n0 = blockIdx.x * LIN_BN;
-    const int tid = threadIdx.x;
-    const int ty = tid >> 3;   // 0..7  -> rows ty * 2, ty * 2 + 1
-    const int tx = tid & 7;    // 0..7  -> cols tx * 4 .. tx * 4 + 3
-    // loader mapping: a float4 along K per thread; A tile = 16 rows x 8 float4 = 128 -> 2 per thread,
-    //                                               W tile = 32 rows x 8 float4 = 256 -> 4 per thread
-    const int lrow = tid >> 3, lk = (tid & 7) * 4;
-    float4 ra[2], rw[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ty = lane >> 3;  // rows ty * 4 .. + 3
+    const int tx = lane & 7;   // cols tx * 4 .. + 3
+    const int kspan = K / LIN_WARPS;
+    const int kbeg = warp * kspan, kend = kbeg + kspan;
+    // loader mapping: one float4 along K per (row, lane & 7); 4 rows of 8 float4 per pass
+    const int lrow = lane >> 3, lk = (lane & 7) * 4;
+    float4 ra[4], rw[8];
     auto fetch = [&](int k0) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int r = r0 + lrow + 8 * i;
+        for (int i = 0; i < 4; ++i) {
+            const int r = r0 + lrow + 4 * i;
             ra[i] = (r < R) ? *reinterpret_cast<const float4*>(A + (size_t)r * K + k0 + lk) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int n = n0 + lrow + 8 * i;
+        for (int i = 0; i < 8; ++i) {
+            const int n = n0 + lrow + 4 * i;
             rw[i] = (n < N) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)n * K + k0 + lk)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
-    float acc[2][4] = {};
-    fetch(0);
-    for (int k0 = 0; k0 < K; k0 += LIN_BK) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int r = lrow + 8 * i;
-            sA[lk][r] = ra[i].x; sA[lk + 1][r] = ra[i].y; sA[lk + 2][r] = ra[i].z; sA[lk + 3][r] = ra[i].w;
-        }
+    float acc[4][4] = {};
+    float (*a_s)[LIN_BM + 4] = sA[warp];
+    float (*w_s)[LIN_BN + 4] = sW[warp];
+    fetch(kbeg);
+    for (int k0 = kbeg; k0 < kend; k0 += LIN_BK) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int n = lrow + 8 * i;
-            sW[lk][n] = rw[i].x; sW[lk + 1][n] = rw[i].y; sW[lk + 2][n] = rw[i].z; sW[lk + 3][n] = rw[i].w;
+            const int r = lrow + 4 * i;
+            a_s[lk][r] = ra[i].x; a_s[lk + 1][r] = ra[i].y; a_s[lk + 2][r] = ra[i].z; a_s[lk + 3][r] = ra[i].w;
         }
-        __syncthreads();
-        if (k0 + LIN_BK < K) fetch(k0 + LIN_BK);   // in flight while we compute
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int n = lrow + 4 * i;
+            w_s[lk][n] = rw[i].x; w_s[lk + 1][n] = rw[i].y; w_s[lk + 2][n] = rw[i].z; w_s[lk + 3][n] = rw[i].w;
+        }
+        __syncwarp();
+        if (k0 + LIN_BK < kend) fetch(k0 + LIN_BK);   // in flight while this slab is multiplied
 #pragma unroll
         for (int k = 0; k < LIN_BK; ++k) {
-            const float a0 = sA[k][ty * 2], a1 = sA[k][ty * 2 + 1];
-            const float4 w = *reinterpret_cast<const float4*>(&sW[k][tx * 4]);
-            acc[0][0] = fmaf(a0, w.x, acc[0][0]); acc[0][1] = fmaf(a0, w.y, acc[0][1]);
-            acc[0][2] = fmaf(a0, w.z, acc[0][2]); acc[0][3] = fmaf(a0, w.w, acc[0][3]);
-            acc[1][0] = fmaf(a1, w.x, acc[1][0]); acc[1][1] = fmaf(a1, w.y, acc[1][1]);
-            acc[1][2] = fmaf(a1, w.z, acc[1][2]); acc[1][3] = fmaf(a1, w.w, acc[1][3]);
+            const float4 a = *reinterpret_cast<const float4*>(&a_s[k][ty * 4]);
+            const float4 w = *reinterpret_cast<const float4*>(&w_s[k][tx * 4]);
+            acc[0][0] = fmaf(a.x, w.x, acc[0][0]); acc[0][1] = fmaf(a.x, w.y, acc[0][1]);
+            acc[0][2] = fmaf(a.x, w.z, acc[0][2]); acc[0][3] = fmaf(a.x, w.w, acc[0][3]);
+            acc[1][0] = fmaf(a.y, w.x, acc[1][0]); acc[1][1] = fmaf(a.y, w.y, acc[1][1]);
+            acc[1][2] = fmaf(a.y, w.z, acc[1][2]); acc[1][3] = fmaf(a.y, w.w, acc[1][3]);
+            acc[2][0] = fmaf(a.z, w.x, acc[2][0]); acc[2][1] = fmaf(a.z, w.y, acc[2][1]);
+            acc[2][2] = fmaf(a.z, w.z, acc[2][2]); acc[2][3] = fmaf(a.z, w.w, acc[2][3]);
+            acc[3][0] = fmaf(a.w, w.x, acc[3][0]); acc[3][1] = fmaf(a.w, w.y, acc[3][1]);
+            acc[3][2] = fmaf(a.w, w.z, acc[3][2]); acc[3][3] = fmaf(a.w, w.w, acc[3][3]);
         }
-        __syncthreads();
+        __syncwarp();
     }
+    // combine the four K-partials in a fixed order: red[warp][row][col] aliases the (now dead) weight slabs
+    __syncthreads();
+    float* red = &sW[0][0][0];   // 4 * 16 * 32 floats = 8 KB <= sizeof(sW)
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int r = r0 + ty * 2 + i;
-        if (r >= R) continue;
+    for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(red + ((warp * LIN_BM + ty * 4 + i) * LIN_BN + tx * 4)) =
+            make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    __syncthreads();
+    // 512 outputs, 128 threads: thread t finishes row t / 8, cols (t % 8) * 4 .. + 3
+    const int orow = threadIdx.x >> 3, ocol = (threadIdx.x & 7) * 4;
+    float4 v = *reinterpret_cast<const float4*>(red + (orow * LIN_BN + ocol));
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tx * 4 + j;
-            if (n >= N) continue;
-            float v = acc[i][j];
-            if (bias != nullptr) v += bias[n];
-            if (ACT == LIN_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));  // nn.GELU() exact
-            if (residual != nullptr) v += residual[(size_t)r * N + n];
-            C[(size_t)r * N + n] = v;
-        }
+    for (int wv = 1; wv < LIN_WARPS; ++wv) {
+        const float4 t = *reinterpret_cast<const float4*>(red + ((wv * LIN_BM + orow) * LIN_BN + ocol));
+        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    }
+    const int r = r0 + orow;
+    if (r >= R) return;
+    float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = n0 + ocol + j;
+        if (n >= N) continue;
+        float y = o[j];
+        if (bias != nullptr) y += bias[n];
+        if (ACT == LIN_GELU) y = 0.5f * y * (1.0f + erff(y * 0.70710678118654752440f));  // nn.GELU() exact
+        if (residual != nullptr) y += residual[(size_t)r * N + n];
+        C[(size_t)r * N + n] = y;
     }
 }
 
