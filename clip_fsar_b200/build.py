@@ -6,8 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "fsar.cu")
 OUT = os.path.join(HERE, "libfsar_sm100.so")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("fsar.cu", "ptx.cuh", "gemm_tcgen05.cuh", "vit_kernels.cuh",
-                                                "head_kernels.cuh")] + [os.path.join(HERE, "..", "include", "fsar.h")]
+DEPS = sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))
+              if f.endswith((".cu", ".cuh"))) + [os.path.join(HERE, "..", "include", "fsar.h")]
 
 
 def nvcc_cmd(extra=()):

@@ -20,6 +20,8 @@
 #include <vector>
 
 #include "../../include/fsar.h"
+#include "attention_tcgen05.cuh"
+#include "gemm_pair_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
 #include "head_kernels.cuh"
 #include "vit_kernels.cuh"
@@ -101,6 +103,8 @@ struct fsar_handle {
     // ---- instrumentation
     int64_t launches = 0;
     bool profiling = false;
+    bool single_cta_gemm = false;   // FSAR_GEMM_SINGLE=1: one CTA per 128 x 256 tile instead of CTA pairs (A/B testing)
+    bool legacy_attention = false;  // FSAR_LEGACY_ATTENTION=1: mma.sync attention core also for L <= 208 (A/B testing)
     std::vector<ProfRec> prof;
 };
 
@@ -209,6 +213,32 @@ int launch_gemm_inst(fsar_handle* h, const CUtensorMap& ta, const CUtensorMap& t
     return check_launch(h, "gemm_tn_tcgen05_kernel");
 }
 
+template <int EPI>
+int launch_gemm_pair_inst(fsar_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                          const GemmParams& p, cudaStream_t st) {
+    auto kern = gemm_tn_tcgen05_pair_kernel<EPI, T16>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CU_OK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
+        attr_done = true;
+    }
+    const int tiles = ((p.M + 255) / 256) * ((p.N + GEMM2_BN - 1) / GEMM2_BN);
+    const int pairs = tiles < h->sms / 2 ? tiles : h->sms / 2;
+    kern<<<2 * pairs, GEMM_THREADS, GEMM2_SMEM_BYTES, st>>>(ta, tb, tc, p);   // __cluster_dims__(2, 1, 1)
+    return check_launch(h, "gemm_tn_tcgen05_pair_kernel");
+}
+
+int launch_gemm_pair(fsar_handle* h, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                     const GemmParams& p, cudaStream_t st) {
+    switch (epi) {
+        case EPI_STORE16: return launch_gemm_pair_inst<EPI_STORE16>(h, ta, tb, tc, p, st);
+        case EPI_QGELU16: return launch_gemm_pair_inst<EPI_QGELU16>(h, ta, tb, tc, p, st);
+        case EPI_RESID32: return launch_gemm_pair_inst<EPI_RESID32>(h, ta, tb, tc, p, st);
+        case EPI_STORE32: return launch_gemm_pair_inst<EPI_STORE32>(h, ta, tb, tc, p, st);
+    }
+    return fail(h, FSAR_E_INVALID, "unknown GEMM epilogue %d", epi);
+}
+
 template <int BN>
 int launch_gemm_bn(fsar_handle* h, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                    const GemmParams& p, cudaStream_t st) {
@@ -233,10 +263,12 @@ int gemm(fsar_handle* h, int cls, const T16* a, const T16* w, const float* bias,
     const int bn = (N >= 256) ? 256 : ((N >= 128) ? 128 : 64);
     const bool out16 = (epi == EPI_STORE16 || epi == EPI_QGELU16);
     CUtensorMap ta, tb, tc;
+    const bool pair = (bn == 256) && !h->single_cta_gemm;   // CTA pairs (cta_group::2, 256 x 256 tiles)
     RET_IF(get_tmap(h, a, M, K, GEMM_BM, GEMM_BK, 0, &ta));
-    RET_IF(get_tmap(h, w, N, K, bn, GEMM_BK, 0, &tb));
+    RET_IF(get_tmap(h, w, N, K, pair ? GEMM2_BN / 2 : bn, GEMM_BK, 0, &tb));
     RET_IF(get_tmap(h, out, M, N, 32, out16 ? 64 : 32, out16 ? 0 : 1, &tc));
     Scope s(h, st, cls, 2.0 * M * N * K, 0.0);
+    if (pair) return launch_gemm_pair(h, epi, ta, tb, tc, p, st);
     if (bn == 256) return launch_gemm_bn<256>(h, epi, ta, tb, tc, p, st);
     if (bn == 128) return launch_gemm_bn<128>(h, epi, ta, tb, tc, p, st);
     return launch_gemm_bn<64>(h, epi, ta, tb, tc, p, st);
@@ -281,10 +313,29 @@ int layernorm(fsar_handle* h, const float* x, void* out, const float* g, const f
 
 int attention(fsar_handle* h, const T16* qkv, int n_frames, int L, int heads, T16* out, cudaStream_t st) {
     const int D = heads * ATT_HD;
-    const dim3 grid((L + ATT_QROWS - 1) / ATT_QROWS, heads, n_frames);
     const float scale_log2e = 0.125f * 1.4426950408889634f;  // head_dim ** -0.5 * log2(e)
     Scope s(h, st, FSAR_K_ATTENTION, 4.0 * n_frames * heads * (double)L * L * ATT_HD,
             (double)n_frames * L * D * 2.0 * 4.0);
+    if (L <= ATT5_MAX_KEYS && !h->legacy_attention) {
+        // tcgen05 / TMEM path: S and O accumulate in tensor memory, one softmax thread per query row
+        static bool done5 = false;
+        if (!done5) {
+            CU_OK(h, cudaFuncSetAttribute(attention_tcgen05_kernel<T16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          ATT5_SMEM_BYTES));
+            done5 = true;
+        }
+        Att5Params ap{};
+        ap.n_frames = n_frames; ap.L = L; ap.heads = heads; ap.D = D;
+        ap.LK = round_up(L, 16); ap.n_mtiles = (L + 127) / 128; ap.scale_log2e = scale_log2e; ap.out = out;
+        CUtensorMap tq, tkv;
+        RET_IF(get_tmap(h, qkv, n_frames * L, 3 * D, 128, 64, 0, &tq));
+        RET_IF(get_tmap(h, qkv, n_frames * L, 3 * D, ap.LK, 64, 0, &tkv));
+        const int items = n_frames * heads;
+        const int grid5 = items < h->sms ? items : h->sms;
+        attention_tcgen05_kernel<T16><<<grid5, ATT5_THREADS, ATT5_SMEM_BYTES, st>>>(tq, tkv, ap);
+        return check_launch(h, "attention_tcgen05_kernel");
+    }
+    const dim3 grid((L + ATT_QROWS - 1) / ATT_QROWS, heads, n_frames);
     if (L <= 208) {
         static bool done = false;
         if (!done) {
@@ -696,6 +747,12 @@ int fsar_create(const fsar_config* cfg, fsar_handle** out) {
     h->tokens = h->grid * h->grid + 1;
     h->patch_k = 3 * c.patch_size * c.patch_size;
     h->patch_kp = round_up(h->patch_k, GEMM_BK);
+    {
+        const char* e = getenv("FSAR_LEGACY_ATTENTION");
+        h->legacy_attention = (e != nullptr && e[0] == '1');
+        e = getenv("FSAR_GEMM_SINGLE");
+        h->single_cta_gemm = (e != nullptr && e[0] == '1');
+    }
     int rc = 0;
     do {
         if (cudaSetDevice(c.device) != cudaSuccess) { rc = fail(nullptr, FSAR_E_CUDA, "cudaSetDevice(%d) failed", c.device); break; }

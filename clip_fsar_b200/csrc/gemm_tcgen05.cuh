@@ -70,6 +70,96 @@ __device__ __forceinline__ float quick_gelu(float v) {
     return __fdividef(v, 1.0f + __expf(-1.702f * v));
 }
 
+// Epilogue of one 128-row x BN-column accumulator tile for ONE warp: lanes [32 q, 32 q + 32) of TMEM (t_base already
+// points at them), the column chunks of parity `half`. tcgen05.ld -> fused tail -> 128B-swizzled smem staging tile ->
+// TMA store / reduce-add. `release()` hands the accumulator back to the MMA warp as soon as this warp has read its share.
+template <int BN, int EPI, typename T16, typename Release>
+__device__ __forceinline__ void gemm_epilogue_tile(uint32_t t_base, int row0, int col_base, const GemmParams& p,
+                                                   const CUtensorMap* tmC, uint8_t* stage_ptr, uint32_t row_addr,
+                                                   uint32_t sw, int half, int lane, Release release) {
+    constexpr bool kOut16 = (EPI == EPI_STORE16 || EPI == EPI_QGELU16);
+    constexpr int CHUNK = kOut16 ? 64 : 32;
+    constexpr int NCH = BN / CHUNK;
+    bool released = false;
+
+#pragma unroll 1
+    for (int c = half; c < NCH; c += 2) {
+        const int col0 = col_base + c * CHUNK;
+        uint32_t w[32];  // the staging row of this thread: 128 B
+        if (kOut16) {
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32b_x32(t_base + c * 64, r0);
+            tmem_ld_32x32b_x32(t_base + c * 64 + 32, r1);
+            tc_wait_ld();
+            if (c + 2 >= NCH) {  // this warp's share of the accumulator is read: hand it back early
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) release();
+                released = true;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                if (p.bias != nullptr) {
+                    if (col0 + j < p.N) b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                    if (col0 + 32 + j < p.N) b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 32 + j));
+                }
+                float v0 = __uint_as_float(r0[j]) + b0.x, v1 = __uint_as_float(r0[j + 1]) + b0.y;
+                float v2 = __uint_as_float(r0[j + 2]) + b0.z, v3 = __uint_as_float(r0[j + 3]) + b0.w;
+                float u0 = __uint_as_float(r1[j]) + b1.x, u1 = __uint_as_float(r1[j + 1]) + b1.y;
+                float u2 = __uint_as_float(r1[j + 2]) + b1.z, u3 = __uint_as_float(r1[j + 3]) + b1.w;
+                if (EPI == EPI_QGELU16) {
+                    v0 = quick_gelu(v0); v1 = quick_gelu(v1); v2 = quick_gelu(v2); v3 = quick_gelu(v3);
+                    u0 = quick_gelu(u0); u1 = quick_gelu(u1); u2 = quick_gelu(u2); u3 = quick_gelu(u3);
+                }
+                w[j / 2] = pack2<T16>(v0, v1);
+                w[j / 2 + 1] = pack2<T16>(v2, v3);
+                w[16 + j / 2] = pack2<T16>(u0, u1);
+                w[16 + j / 2 + 1] = pack2<T16>(u2, u3);
+            }
+        } else {
+            tmem_ld_32x32b_x32(t_base + c * 32, w);
+            tc_wait_ld();
+            if (c + 2 >= NCH) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) release();
+                released = true;
+            }
+            if (p.bias != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (col0 + j < p.N) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                        w[j] = __float_as_uint(__uint_as_float(w[j]) + b.x);
+                        w[j + 1] = __float_as_uint(__uint_as_float(w[j + 1]) + b.y);
+                        w[j + 2] = __float_as_uint(__uint_as_float(w[j + 2]) + b.z);
+                        w[j + 3] = __float_as_uint(__uint_as_float(w[j + 3]) + b.w);
+                    }
+                }
+            }
+        }
+        // the staging buffer must have been drained by the previous TMA store of this warp
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            st_shared_v4(row_addr + ((uint32_t(j) ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && row0 < p.M && col0 < p.N) {
+            if (EPI == EPI_RESID32) tma_reduce_add_2d(tmC, stage_ptr, col0, row0);
+            else tma_store_2d(tmC, stage_ptr, col0, row0);
+            tma_store_commit();
+        }
+    }
+    if (!released) {  // no chunk for this warp in such a narrow tile: still release the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) release();
+    }
+}
+
 template <int BN, int EPI, typename T16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -94,7 +184,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = warp_idx_uniform();
     const int lane = threadIdx.x & 31;
 
     const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
@@ -129,43 +219,46 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                // n-major tile order: the CTAs of one wave share few weight tiles and stream distinct A tiles
-                const int n_blk = tile / m_tiles;
-                const int m_blk = tile - n_blk * m_tiles;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        // The whole warp walks the loop (warp-uniform control flow keeps addresses / coordinates in uniform
+        // registers); one elected lane issues.
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            // n-major tile order: the CTAs of one wave share few weight tiles and stream distinct A tiles
+            const int n_blk = tile / m_tiles;
+            const int m_blk = tile - n_blk * m_tiles;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                     tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
                     tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                }
+                __syncwarp();
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(GEMM_BM, BN, kBf16, false, false);
-            constexpr uint64_t desc_hi = umma_smem_desc_hi(0, 1024, UMMA_LAYOUT_SW128);  // SBO = 8 rows x 128 B
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+        // ------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane)
+        constexpr uint32_t idesc = umma_idesc_f16(GEMM_BM, BN, kBf16, false, false);
+        constexpr uint64_t desc_hi = umma_smem_desc_hi(0, 1024, UMMA_LAYOUT_SW128);  // SBO = 8 rows x 128 B
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::A_BYTES);
-                    const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::B_BYTES);
+                const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::A_BYTES);
+                const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::B_BYTES);
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; ++k) {
                         // advance 16 elements (32 B) along K inside the 128 B swizzle atom
@@ -174,16 +267,17 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                         umma_f16_ss(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                    if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);  // accumulator ready for the epilogue
                 }
-                umma_commit(&tfull_bar[acc]);  // accumulator ready for the epilogue
-                if (++acc == 2) {
-                    acc = 0;
-                    acc_phase ^= 1;
+                __syncwarp();
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
                 }
+            }
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
             }
         }
     } else if (warp >= 4) {
@@ -193,7 +287,6 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         uint8_t* stage_ptr = smem_stage + (warp - 4) * GEMM_STAGE_TILE_BYTES;
         const uint32_t row_addr = smem_u32(stage_ptr) + lane * 128;  // this thread's row inside the staging tile
         const uint32_t sw = uint32_t(lane & 7);                      // 128B swizzle: 16-byte chunk index ^= row % 8
-        constexpr int NCH = BN / CHUNK;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -203,84 +296,8 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_base = tmem_base + acc * BN + (uint32_t(q * 32) << 16);
-            bool released = false;
-
-#pragma unroll 1
-            for (int c = half; c < NCH; c += 2) {
-                const int col0 = n_blk * BN + c * CHUNK;
-                uint32_t w[32];  // the staging row of this thread: 128 B
-                if (kOut16) {
-                    uint32_t r0[32], r1[32];
-                    tmem_ld_32x32b_x32(t_base + c * 64, r0);
-                    tmem_ld_32x32b_x32(t_base + c * 64 + 32, r1);
-                    tc_wait_ld();
-                    if (c + 2 >= NCH) {  // this warp's share of the accumulator is read: hand it back early
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                        released = true;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-                        if (p.bias != nullptr) {
-                            if (col0 + j < p.N) b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                            if (col0 + 32 + j < p.N) b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 32 + j));
-                        }
-                        float v0 = __uint_as_float(r0[j]) + b0.x, v1 = __uint_as_float(r0[j + 1]) + b0.y;
-                        float v2 = __uint_as_float(r0[j + 2]) + b0.z, v3 = __uint_as_float(r0[j + 3]) + b0.w;
-                        float u0 = __uint_as_float(r1[j]) + b1.x, u1 = __uint_as_float(r1[j + 1]) + b1.y;
-                        float u2 = __uint_as_float(r1[j + 2]) + b1.z, u3 = __uint_as_float(r1[j + 3]) + b1.w;
-                        if (EPI == EPI_QGELU16) {
-                            v0 = quick_gelu(v0); v1 = quick_gelu(v1); v2 = quick_gelu(v2); v3 = quick_gelu(v3);
-                            u0 = quick_gelu(u0); u1 = quick_gelu(u1); u2 = quick_gelu(u2); u3 = quick_gelu(u3);
-                        }
-                        w[j / 2] = pack2<T16>(v0, v1);
-                        w[j / 2 + 1] = pack2<T16>(v2, v3);
-                        w[16 + j / 2] = pack2<T16>(u0, u1);
-                        w[16 + j / 2 + 1] = pack2<T16>(u2, u3);
-                    }
-                } else {
-                    tmem_ld_32x32b_x32(t_base + c * 32, w);
-                    tc_wait_ld();
-                    if (c + 2 >= NCH) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                        released = true;
-                    }
-                    if (p.bias != nullptr) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            if (col0 + j < p.N) {
-                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                                w[j] = __float_as_uint(__uint_as_float(w[j]) + b.x);
-                                w[j + 1] = __float_as_uint(__uint_as_float(w[j + 1]) + b.y);
-                                w[j + 2] = __float_as_uint(__uint_as_float(w[j + 2]) + b.z);
-                                w[j + 3] = __float_as_uint(__uint_as_float(w[j + 3]) + b.w);
-                            }
-                        }
-                    }
-                }
-                // the staging buffer must have been drained by the previous TMA store of this warp
-                if (lane == 0) tma_store_wait_read<0>();
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    st_shared_v4(row_addr + ((uint32_t(j) ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0 && row0 < p.M && col0 < p.N) {
-                    if (EPI == EPI_RESID32) tma_reduce_add_2d(&tmC, stage_ptr, col0, row0);
-                    else tma_store_2d(&tmC, stage_ptr, col0, row0);
-                    tma_store_commit();
-                }
-            }
-            if (!released) {  // no chunk for this warp in such a narrow tile: still release the accumulator
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-            }
+            gemm_epilogue_tile<BN, EPI, T16>(t_base, row0, n_blk * BN, p, &tmC, stage_ptr, row_addr, sw, half, lane,
+                                             [&]() { mbar_arrive(&tempty_bar[acc]); });
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;

@@ -111,6 +111,31 @@ def gemm():
 
 
 @guarded
+def gemm_peak():
+    """Steady-state rate of the GEMM main loop: shapes with whole waves and a long K so that ramp/tail/epilogue vanish."""
+    eng, g = make_engine("tiny")
+    dt = eng.operand_dtype
+    for (M, N, K) in ((18944, 256, 16384), (18944, 512, 8192), (18944, 2304, 768), (18944, 768, 768), (18944, 3072, 768),
+                      (18944, 768, 3072), (15760, 2304, 768), (15760, 768, 3072)):
+        a = (torch.randn(M, K, device=DEV) * 0.1).to(dt)
+        w = (torch.randn(N, K, device=DEV) * 0.1).to(dt)
+        out = torch.zeros(M, N, device=DEV, dtype=dt)
+        for _ in range(3):
+            eng.op_gemm(a, w, None, L.EPI_STORE16, out=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        n = 20
+        e0.record()
+        for _ in range(n):
+            eng.op_gemm(a, w, None, L.EPI_STORE16, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        report("gemm_peak_%dx%dx%d" % (M, N, K), ms=ms, tflops=2.0 * M * N * K / ms / 1e9,
+               single=os.environ.get("FSAR_GEMM_SINGLE", "0"))
+
+
+@guarded
 def attention():
     eng, g = make_engine("tiny")
     dt = eng.operand_dtype
@@ -251,7 +276,7 @@ def full():
 
 
 if __name__ == "__main__":
-    groups = dict(basic=basic, gemm=gemm, attention=attention, vit=vit, head=head, episode=episode, full=full)
+    groups = dict(basic=basic, gemm=gemm, gemm_peak=gemm_peak, attention=attention, vit=vit, head=head, episode=episode, full=full)
     for name in sys.argv[1:] or list(groups):
         report("group", name=name, gpu=torch.cuda.get_device_name(0))
         groups[name]()
