@@ -103,6 +103,7 @@ struct fsar_handle {
     // ---- instrumentation
     int64_t launches = 0;
     bool profiling = false;
+    size_t l2_persist_bytes = 0, l2_window_max = 0;   // L2 set-aside for the residual stream (0 = disabled)
     bool single_cta_gemm = false;   // FSAR_GEMM_SINGLE=1: one CTA per 128 x 256 tile instead of CTA pairs (A/B testing)
     bool legacy_attention = false;  // FSAR_LEGACY_ATTENTION=1: mma.sync attention core also for L <= 208 (A/B testing)
     std::vector<ProfRec> prof;
@@ -497,10 +498,30 @@ bool ready(fsar_handle* h, bool need_text) {
 
 // ---------------------------------------------------------------- the ViT frame encoder
 // Encodes `n` frames whose patches are already gathered into h->patches16 rows [0, n * G * G).
+// The fp32 residual stream (48 MB for an 80-frame pass) is touched four times per layer (LN1, out-proj reduce-add,
+// LN2, c_proj reduce-add) with > 100 MB of other traffic in between, so by default it round-trips to HBM every time.
+// An L2 access-policy window marks it persisting (and everything else keeps the normal policy) for the kernels of
+// this pass; the window is removed again before returning so the caller's stream is left as it was.
+void set_l2_window(fsar_handle* h, cudaStream_t st, void* ptr, size_t bytes) {
+    if (h->l2_persist_bytes == 0) return;
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    if (ptr != nullptr && bytes > 0) {
+        if (bytes > h->l2_window_max) bytes = h->l2_window_max;
+        attr.accessPolicyWindow.base_ptr = ptr;
+        attr.accessPolicyWindow.num_bytes = bytes;
+        attr.accessPolicyWindow.hitRatio = bytes <= h->l2_persist_bytes ? 1.0f : float(double(h->l2_persist_bytes) / double(bytes));
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    }
+    if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+}
+
 int vit_encode_gathered(fsar_handle* h, int n, float* feats_out, cudaStream_t st) {
     const fsar_config& c = h->cfg;
     const int D = c.width, L = h->tokens, G2 = h->grid * h->grid;
     const int M = n * L;
+    set_l2_window(h, st, h->x32, sizeof(float) * (size_t)M * D);
     // conv1 as a GEMM into a scratch [n * G * G, D] fp32 (the MLP hidden buffer is free at this point) ...
     float* patch32 = reinterpret_cast<float*>(h->h16);
     RET_IF(gemm(h, FSAR_K_GEMM_PATCH, h->patches16, W16(h, "backbone.conv1.weight"), nullptr, patch32, n * G2, D,
@@ -533,6 +554,7 @@ int vit_encode_gathered(fsar_handle* h, int n, float* feats_out, cudaStream_t st
             feats_out, n, L, D, c.embed_dim, 1e-5f);
         RET_IF(check_launch(h, "final_proj_kernel"));
     }
+    set_l2_window(h, st, nullptr, 0);
     return 0;
 }
 
@@ -763,6 +785,22 @@ int fsar_create(const fsar_config* cfg, fsar_handle** out) {
             break;
         }
         h->encode = reinterpret_cast<fsar_handle::EncodeFn>(fn);
+        {   // L2 set-aside for the residual stream (FSAR_NO_L2_PERSIST=1 disables it)
+            const char* e = getenv("FSAR_NO_L2_PERSIST");
+            int max_persist = 0, max_window = 0;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c.device);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c.device);
+            if (!(e != nullptr && e[0] == '1') && max_persist > 0 && max_window > 0) {
+                size_t want = sizeof(float) * (size_t)c.max_frames * h->tokens * c.width;
+                if (want > (size_t)max_persist) want = (size_t)max_persist;
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+                    h->l2_persist_bytes = want;
+                    h->l2_window_max = (size_t)max_window;
+                } else {
+                    cudaGetLastError();
+                }
+            }
+        }
         if ((rc = alloc_weights(h)) != 0) break;
         if ((rc = alloc_workspace(h)) != 0) break;
     } while (0);

@@ -224,9 +224,10 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            // n-major tile order: the CTAs of one wave share few weight tiles and stream distinct A tiles
-            const int n_blk = tile / m_tiles;
-            const int m_blk = tile - n_blk * m_tiles;
+            // m-major tile order: the n-tiles of one row block run concurrently on neighbouring CTAs, so an A tile is
+            // fetched from HBM once and re-used out of L2 (the weights are a few MB and stay L2-resident anyway)
+            const int m_blk = tile / n_tiles;
+            const int n_blk = tile - m_blk * n_tiles;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (elect_one()) {
@@ -290,8 +291,8 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int n_blk = tile / m_tiles;
-            const int m_blk = tile - n_blk * m_tiles;
+            const int m_blk = tile / n_tiles;
+            const int n_blk = tile - m_blk * n_tiles;
             const int row0 = m_blk * GEMM_BM + q * 32;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
