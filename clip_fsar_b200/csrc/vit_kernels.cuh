@@ -127,9 +127,10 @@ layernorm_kernel(const float* x, void* out, const float* __restrict__ gamma, con
 
 // ------------------------------------------------------------------------------------------------
 // ln_post(x[:, 0, :]) @ proj  (few_shot.py:683-686). proj is [D, E] fp32.
-// grid = (ceil(frames / FPC), E / FINAL_COLS); 256 threads = FINAL_COLS columns x 2 halves of the D reduction.
+// grid = (ceil(frames / FPC), E / FINAL_COLS); 256 threads = FINAL_COLS columns x FINAL_KSPLIT slices of the D reduction.
 constexpr int FINAL_FPC = 4;
-constexpr int FINAL_COLS = 128;
+constexpr int FINAL_COLS = 64;
+constexpr int FINAL_KSPLIT = 256 / FINAL_COLS;
 __global__ void __launch_bounds__(256)
 final_proj_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                   const float* __restrict__ proj, float* __restrict__ out, int n_frames, int tokens, int D, int E,
@@ -178,31 +179,35 @@ final_proj_kernel(const float* __restrict__ x, const float* __restrict__ gamma, 
         for (int d = threadIdx.x; d < D; d += blockDim.x)
             sm[f * D + d] = (sm[f * D + d] - mean[f]) * rstd[f] * gamma[d] + beta[d];
     __syncthreads();
-    // projection: column e of this CTA's slice, half `kh` of the D reduction; halves are combined through smem
-    __shared__ float part[FINAL_FPC][FINAL_COLS];
-    const int e = blockIdx.y * FINAL_COLS + (threadIdx.x & (FINAL_COLS - 1));
-    const int kh = threadIdx.x / FINAL_COLS;  // 0 or 1
-    const int dlo = kh * (D >> 1), dhi = dlo + (D >> 1);
+    // projection: column e of this CTA's slice, slice `kh` of the D reduction; slices are combined through smem
+    __shared__ float part[FINAL_KSPLIT][FINAL_FPC][FINAL_COLS];
+    const int ce = threadIdx.x & (FINAL_COLS - 1);
+    const int e = blockIdx.y * FINAL_COLS + ce;
+    const int kh = threadIdx.x / FINAL_COLS;
+    const int dspan = D / FINAL_KSPLIT;
+    const int dlo = kh * dspan, dhi = dlo + dspan;
     float acc[FINAL_FPC];
 #pragma unroll
     for (int f = 0; f < FINAL_FPC; ++f) acc[f] = 0.f;
     if (e < E) {
-#pragma unroll 4
+#pragma unroll 8
         for (int d = dlo; d < dhi; ++d) {
             const float w = __ldg(proj + (size_t)d * E + e);
 #pragma unroll
             for (int f = 0; f < FINAL_FPC; ++f) acc[f] = fmaf(sm[f * D + d], w, acc[f]);
         }
     }
-    if (kh == 1) {
 #pragma unroll
-        for (int f = 0; f < FINAL_FPC; ++f) part[f][threadIdx.x & (FINAL_COLS - 1)] = acc[f];
-    }
+    for (int f = 0; f < FINAL_FPC; ++f) part[kh][f][ce] = acc[f];
     __syncthreads();
     if (kh == 0 && e < E) {
 #pragma unroll
-        for (int f = 0; f < FINAL_FPC; ++f)
-            if (f0 + f < n_frames) out[(size_t)(f0 + f) * E + e] = acc[f] + part[f][threadIdx.x];
+        for (int f = 0; f < FINAL_FPC; ++f) {
+            float v = part[0][f][ce];
+#pragma unroll
+            for (int k = 1; k < FINAL_KSPLIT; ++k) v += part[k][f][ce];
+            if (f0 + f < n_frames) out[(size_t)(f0 + f) * E + e] = v;
+        }
     }
 }
 

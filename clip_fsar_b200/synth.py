@@ -14,6 +14,8 @@ GEOMETRIES = {
     # small towers with the same structure, for tests that must finish in seconds on CPU
     "tiny": dict(image_size=32, patch_size=16, width=128, layers=2, heads=2, embed_dim=128),
     "small": dict(image_size=64, patch_size=16, width=256, layers=3, heads=4, embed_dim=256),
+    # ViT-L/14 token / width geometry (257 tokens, width 1024, patch K = 588) with 2 layers, for parity tests
+    "l14-2layer": dict(image_size=224, patch_size=14, width=1024, layers=2, heads=16, embed_dim=768),
 }
 
 

@@ -36,6 +36,16 @@ def quick_gelu(x):
     return x * torch.sigmoid(1.702 * x)
 
 
+def quick_gelu_16(x, dt):
+    """QuickGELU as the CUDA epilogue evaluates it when operands are 16-bit: x sigmoid(1.702 x) = h + h tanh(0.851 x),
+    h = x / 2, in packed 16-bit arithmetic (every intermediate rounded to `dt`, the final fma rounded once)."""
+    r = lambda v: v.to(dt).float()
+    x16 = r(x)
+    t = r(torch.tanh(r(r(torch.tensor(0.851)) * x16)))
+    h = r(0.5 * x16)
+    return r(h * t + h)
+
+
 def gelu_erf(x):
     """nn.GELU() (exact erf form) used by FeedForward, few_shot.py:1648."""
     return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
@@ -78,7 +88,8 @@ def residual_block(x, sd, p, heads, dt=None):
     o = _rnd(o.transpose(1, 2).reshape(n, L, D), dt)
     x = x + o @ _rnd(sd[p + "attn.out_proj.weight"], dt).T + sd[p + "attn.out_proj.bias"]
     y = _rnd(layer_norm(x, sd[p + "ln_2.weight"], sd[p + "ln_2.bias"]), dt)
-    hdn = _rnd(quick_gelu(y @ _rnd(sd[p + "mlp.c_fc.weight"], dt).T + sd[p + "mlp.c_fc.bias"]), dt)
+    pre = y @ _rnd(sd[p + "mlp.c_fc.weight"], dt).T + sd[p + "mlp.c_fc.bias"]
+    hdn = quick_gelu(pre) if dt is None else quick_gelu_16(pre, dt)
     return x + hdn @ _rnd(sd[p + "mlp.c_proj.weight"], dt).T + sd[p + "mlp.c_proj.bias"]
 
 

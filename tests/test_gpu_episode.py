@@ -85,6 +85,25 @@ def test_episode_matches_16bit_emulating_oracle_tightly(lib, name):
     e.close()
 
 
+def test_vit_l14_geometry_against_oracle(lib):
+    """BASELINE.json configs[3] names ViT-L/14 (257 tokens, width 1024, 14x14 patches -> K = 588 padded to 640):
+    the reference head has no branch for it, so the oracle restatement is the checker."""
+    from clip_fsar_b200 import synth
+    from oracle import fsar_oracle as O
+    g = synth.full_geometry("l14-2layer")
+    sd = synth.synth_state_dict(g, 3)
+    e = lib.Engine(**dict(g, max_frames=6, max_videos=4, max_tokens=4, max_classes=8, otam_lambda=0.5, device=0))
+    e.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    frames = torch.from_numpy(synth.synth_episode(2, 1, 1, 4, 224, 8, 11)["support_set"])      # 8 frames, 2 passes
+    ref32 = O.vit_forward(sd, g, frames)
+    ref16 = O.vit_forward(sd, g, frames, operand_dtype=e.operand_dtype)
+    out = e.vit_forward(frames.to(DEV))
+    assert rel_l2(out, ref32) < 5e-3 and rel_l2(out, ref16) < 1e-3
+    x = torch.randn(3, 5, g["embed_dim"])
+    assert rel_l2(e.modulate(x.to(DEV)), O.modulator(sd, g, x)) < 5e-6
+    e.close()
+
+
 def test_host_buffer_entry_point_equals_device_entry_point(lib):
     meta, _ = load_golden("tiny_5w5s_nomerge")
     g, sd, tt, te, task = regenerate(meta)

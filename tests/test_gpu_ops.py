@@ -58,7 +58,9 @@ def test_tcgen05_gemm_all_epilogues(eng, lib, M, N, K):
     assert rel_l2(eng.op_gemm(a, w, bias, lib.EPI_STORE32), ref) < 1e-5        # accumulation-order noise only
     assert rel_l2(eng.op_gemm(a, w, None, lib.EPI_STORE32), ref - bias) < 1e-5
     assert rel_l2(eng.op_gemm(a, w, bias, lib.EPI_STORE16), ref) < 4e-4        # + one 16-bit rounding
-    assert rel_l2(eng.op_gemm(a, w, bias, lib.EPI_QGELU16), ref * torch.sigmoid(1.702 * ref)) < 5e-4
+    # QuickGELU is evaluated as h + h tanh(0.851 x) in packed 16-bit arithmetic (one MUFU per two elements):
+    # three 16-bit roundings + tanh.approx instead of one rounding
+    assert rel_l2(eng.op_gemm(a, w, bias, lib.EPI_QGELU16), ref * torch.sigmoid(1.702 * ref)) < 1.5e-3
     x0 = torch.randn(M, N, device=DEV)
     assert rel_l2(eng.op_gemm(a, w, bias, lib.EPI_RESID32, out=x0.clone()), ref + x0) < 1e-5
 
