@@ -5,10 +5,12 @@ random-init weights, synthetic frames. A step = one episode (80 frames) through 
 CLIP ViT frame encoder -> temporal prototype modulator -> cosine/OTAM head -> logits.
 
   value : whole-job episodes/s with the inputs already resident in HBM (a pool of distinct episodes larger than
-          L2 is cycled, so no step re-reads its inputs from cache); device-timed, max over ranks.
-  e2e   : the same metric through the C-ABI host entry points (fsar_episode_submit_host / collect_host): HOST
-          pinned buffers in, logits on the host out, H2D + D2H inside the timed region, copies of episode i+1
-          overlapped with the compute of episode i (two slots).
+          L2 is cycled, so no step re-reads its inputs from cache); device-timed, max over ranks. Episodes go
+          through fsar_episodes_forward --batch at a time (default 6 = 480 frames = five 96-frame ViT passes, which
+          makes every GEMM a whole number of tile waves); --batch 1 gives the one-episode-per-call figure.
+  e2e   : the same metric through the C-ABI host entry points (fsar_episodes_submit_host / collect_host): HOST
+          pinned buffers in, logits on the host out, H2D + D2H inside the timed region, copies of call i+1
+          overlapped with the compute of call i (two slots).
   roofline     : the tcgen05 GEMM kernel (95 % of the FLOPs): algorithmic FLOPs / CUDA-event time of its launches.
   cpu_baseline : the CPU oracle (a port of the reference forward) on this box's host cores, bounded sample.
 
@@ -148,7 +150,10 @@ def main():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pool", type=int, default=4, help="distinct resident episodes cycled (4 x 48 MB > 126 MB L2)")
+    ap.add_argument("--batch", type=int, default=6,
+                    help="episodes per fsar_episodes_* call; their 80-frame sets are regrouped into 96-frame ViT passes "
+                         "(whole waves of 256x256 tiles on 148 SMs). 1 = one episode per call")
+    ap.add_argument("--pool", type=int, default=6, help="distinct resident episodes cycled (6 x 48 MB > 126 MB L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -158,6 +163,10 @@ def main():
         return reference_arm(args, rank, world)
     if args.warmup < 3:
         args.warmup = 3
+    B = max(1, args.batch)
+    args.pool = max(args.pool, B)
+    args.steps = -(-args.steps // B) * B          # whole calls
+    n_calls, n_warm_calls = args.steps // B, -(-args.warmup // B)
 
     import torch.distributed as dist
     from clip_fsar_b200 import lib as L
@@ -169,8 +178,9 @@ def main():
 
     g = synth.full_geometry(GEOM)
     n_vid = WAY * (SHOT + QPC)
-    eng = L.Engine(**dict(g, max_frames=n_vid * T, max_videos=n_vid, max_tokens=T, max_classes=max(N_TRAIN, N_TEST),
-                          otam_lambda=0.5, device=local))
+    frames_per_pass = 96 if B > 1 else n_vid * T
+    eng = L.Engine(**dict(g, max_frames=frames_per_pass, max_videos=n_vid, max_tokens=T, max_classes=max(N_TRAIN, N_TEST),
+                          max_batch=B, otam_lambda=0.5, device=local))
     sd_np = synth.synth_state_dict(g, 0, spread=False)
     eng.load_state_dict({k: torch.from_numpy(v) for k, v in sd_np.items()})
     tt = synth.synth_text_features(N_TRAIN, g["embed_dim"], 7)
@@ -186,11 +196,16 @@ def main():
         ep = synth.synth_episode(WAY, SHOT, QPC, T, g["image_size"], N_TEST, 1000 + rank * 1_000_000 + i, structured=False)
         host_pool.append([torch.from_numpy(ep[k]).pin_memory() for k in keys])
         dev_pool.append([t.to(dev) for t in host_pool[-1]])
-    h2d = sum(t.numel() * 4 for t in host_pool[0])
+    h2d = sum(t.numel() * 4 for t in host_pool[0])            # per episode (= per step)
     d2h = (WAY * QPC * WAY + n_vid * N_TRAIN) * 4
 
     def step(i):
-        return eng.episode_forward(*dev_pool[i % args.pool], T, WAY, n_train_classes=N_TRAIN)
+        """One call = B episodes (B steps of the metric)."""
+        eps = [dev_pool[(i * B + j) % args.pool] for j in range(B)]
+        return eng.episodes_forward(eps, T, WAY, n_train_classes=N_TRAIN)
+
+    def host_eps(i):
+        return [host_pool[(i * B + j) % args.pool] for j in range(B)]
 
     def barrier():
         if world > 1:
@@ -205,7 +220,7 @@ def main():
         return ms
 
     # ---------------------------------------------------------------- device-resident throughput
-    for i in range(args.warmup):
+    for i in range(n_warm_calls):
         step(i)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -214,7 +229,7 @@ def main():
     n0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
+    for i in range(n_calls):
         logits, _ = step(i)
     e1.record()
     barrier()
@@ -224,25 +239,27 @@ def main():
     value = args.steps * world / (ms_total / 1e3)
 
     # ---------------------------------------------------------------- end to end through the host entry points
-    out = torch.empty(WAY * QPC, WAY)
-    cl = torch.empty(n_vid, N_TRAIN)
-    for i in range(3):
-        eng.episode_forward_host(*host_pool[i % args.pool], T, WAY, n_train_classes=N_TRAIN)
+    out = torch.empty(B, WAY * QPC, WAY)
+    cl = torch.empty(B, n_vid, N_TRAIN)
+    for i in range(2):
+        eng.episodes_submit_host(0, host_eps(i), T, WAY)
+        eng.episodes_collect_host(0, out, cl)
     barrier()
     t0 = time.perf_counter()
-    eng.episode_submit_host(0, *host_pool[0], T, WAY)
-    for i in range(1, args.steps):
-        eng.episode_submit_host(i & 1, *host_pool[i % args.pool], T, WAY)
-        eng.episode_collect_host((i - 1) & 1, out, cl)
-    eng.episode_collect_host((args.steps - 1) & 1, out, cl)
+    eng.episodes_submit_host(0, host_eps(0), T, WAY)
+    for i in range(1, n_calls):
+        eng.episodes_submit_host(i & 1, host_eps(i), T, WAY)
+        eng.episodes_collect_host((i - 1) & 1, out, cl)
+    eng.episodes_collect_host((n_calls - 1) & 1, out, cl)
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     barrier()
     e2e_value = args.steps * world / (e2e_ms / 1e3)
 
     # ---------------------------------------------------------------- per-kernel device time (CUDA events per launch)
+    NP = 2 * B if B > 1 else 4     # episodes in the profiled pass
     eng.profile_begin()
-    for i in range(4):
+    for i in range(NP // B):
         step(i)
     prof = eng.profile_end()
     pk = peaks()
@@ -255,10 +272,10 @@ def main():
     roofline = {"bound": "tensor", "kernel": "gemm_tn_tcgen05_kernel (patch/QKV/out/fc1/fc2 epilogues)",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
                 "peak_source": pk["src"] + " cuBLAS bf16, sustained (kernel timed inside a long step)",
-                "traffic": None, "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "launches_per_episode": gemm_launches // 4,
+                "traffic": None, "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "launches_per_episode": gemm_launches / NP,
                 "share_of_step": gemm_ms / total_prof_ms if total_prof_ms else None,
-                "flops_per_episode": gemm_flops / 4}
-    kernels = {k: {"ms_per_episode": v["ms"] / 4, "launches_per_episode": v["launches"] // 4,
+                "flops_per_episode": gemm_flops / NP}
+    kernels = {k: {"ms_per_episode": v["ms"] / NP, "launches_per_episode": v["launches"] / NP,
                    "tflops": (v["flops"] / v["ms"] / 1e9 if v["ms"] and v["flops"] else None),
                    "gbs": (v["bytes"] / v["ms"] / 1e6 if v["ms"] and v["bytes"] else None)} for k, v in prof.items()}
 
@@ -285,9 +302,10 @@ def main():
             "config": {"workload": "5-way 1-shot, 1 query/class, 8x224^2 frames, ViT-B/16 random-init, 80 frames/episode",
                        "l2_policy": "inputs larger than L2: %d distinct resident episodes (%.0f MB) cycled" %
                                     (args.pool, args.pool * h2d / 1e6),
+                       "episodes_per_call": B, "frames_per_vit_pass": frames_per_pass,
                        "episodes_per_rank": args.steps, "parallelism": "episodes sharded, dp%d, no data-path collective" % world},
             "e2e": {"value": e2e_value, "unit": "episodes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps, "api": "fsar_episode_submit_host/collect_host (2 slots, pinned)"},
+                    "ms_per_step": e2e_ms / args.steps, "api": "fsar_episodes_submit_host/collect_host (2 slots, pinned host buffers, %d episodes per call)" % B},
             "gpu_launches": launches * world, "clocks": clocks,
             "vit_tflops": flops_ep * args.steps * world / (ms_total / 1e3) / 1e12,
             "vit_frac_of_sustained_peak": flops_ep * args.steps / (ms_total / 1e3) / 1e12 / pk["tf_sustained"],

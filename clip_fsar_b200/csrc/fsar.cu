@@ -65,7 +65,8 @@ struct HostSlot {
     float* logits_pin = nullptr;   // pinned host mirrors
     float* clogits_pin = nullptr;
     cudaEvent_t copied = nullptr, done = nullptr;
-    int n_support = 0, n_target = 0, way = 0, busy = 0;
+    size_t n_logits = 0, n_clogits = 0;
+    int busy = 0;
 };
 
 }  // namespace
@@ -91,6 +92,7 @@ struct fsar_handle {
     int *cls = nullptr, *counts = nullptr;
     // last episode geometry (for fsar_peek)
     int last_S = 0, last_Q = 0, last_T = 0, last_way = 0, last_rows = 0;
+    const float *last_sup = nullptr, *last_tgt = nullptr;
     // ---- TMA
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -473,7 +475,7 @@ int alloc_workspace(fsar_handle* h) {
     const size_t V = c.max_videos, T = c.max_tokens;
     const size_t rows = V * (T + 1);
     const size_t inner = (size_t)c.mod_heads * c.mod_dim_head;
-    RET_IF(dalloc(h, &h->feats, V * T * E));
+    RET_IF(dalloc(h, &h->feats, (size_t)c.max_batch * V * T * E));
     RET_IF(dalloc(h, &h->seq, rows * E));
     RET_IF(dalloc(h, &h->mod_ln, rows * E));
     RET_IF(dalloc(h, &h->mod_qkvbuf, rows * 3 * inner));
@@ -569,26 +571,25 @@ int patch_gather(fsar_handle* h, const float* frames, int n, int row_frame_offse
     return check_launch(h, "patch_gather_kernel");
 }
 
-// Encode frames from up to two device buffers (support frames then target frames) into feats rows
-// [0, n0 + n1), in passes of at most cfg.max_frames frames.
-int vit_encode_segments(fsar_handle* h, const float* f0, int n0, const float* f1, int n1, float* feats, cudaStream_t st) {
+// Encode the frames of a list of device buffers (segment i holds counts[i] frames) into consecutive feats rows, in
+// passes of at most cfg.max_frames frames that ignore segment (video set / episode) boundaries.
+int vit_encode_segments(fsar_handle* h, const float* const* ptrs, const int* counts, int nseg, float* feats,
+                        cudaStream_t st) {
     const fsar_config& c = h->cfg;
     const size_t frame_elems = (size_t)3 * c.image_size * c.image_size;
-    const int total = n0 + n1;
-    int done = 0;
+    int total = 0;
+    for (int i = 0; i < nseg; ++i) total += counts[i];
+    int seg = 0, seg_off = 0, done = 0;
     while (done < total) {
         const int n = (total - done < c.max_frames) ? total - done : c.max_frames;
-        // pieces of this pass: global frame range [done, done + n)
         int filled = 0;
         while (filled < n) {
-            const int g = done + filled;
-            const float* src;
-            int avail;
-            if (g < n0) { src = f0 + (size_t)g * frame_elems; avail = n0 - g; }
-            else { src = f1 + (size_t)(g - n0) * frame_elems; avail = total - g; }
+            while (seg_off == counts[seg]) { ++seg; seg_off = 0; }
+            const int avail = counts[seg] - seg_off;
             const int take = (avail < n - filled) ? avail : n - filled;
-            RET_IF(patch_gather(h, src, take, filled, st));
+            RET_IF(patch_gather(h, ptrs[seg] + (size_t)seg_off * frame_elems, take, filled, st));
             filled += take;
+            seg_off += take;
         }
         RET_IF(vit_encode_gathered(h, n, feats + (size_t)done * c.embed_dim, st));
         done += n;
@@ -641,13 +642,13 @@ int otam_logits(fsar_handle* h, const float* q, const float* protos, int Q, int 
     return check_launch(h, "cos_otam_kernel");
 }
 
-// Everything after the frame encoder: h->feats (support rows then target rows) -> logits, class_logits.
-int head_forward(fsar_handle* h, const float* support_labels, const float* real_support_labels, int S, int Q, int T,
-                 int way, int merge_before, int single_direct, float* logits, float* class_logits, cudaStream_t st) {
+// Everything after the frame encoder: frame features of one episode (support rows, then target rows) -> logits,
+// class_logits.
+int head_forward(fsar_handle* h, const float* sup, const float* tgt, const float* support_labels,
+                 const float* real_support_labels, int S, int Q, int T, int way, int merge_before, int single_direct,
+                 float* logits, float* class_logits, cudaStream_t st) {
     const fsar_config& c = h->cfg;
     const int E = c.embed_dim;
-    const float* sup = h->feats;
-    const float* tgt = h->feats + (size_t)S * T * E;
     {
         Scope s(h, st, FSAR_K_HEAD_MISC, 0.0, 8.0 * S);
         class_index_kernel<<<1, 128, 0, st>>>(support_labels, S, h->cls, h->counts, way);
@@ -680,6 +681,7 @@ int head_forward(fsar_handle* h, const float* support_labels, const float* real_
     }
     RET_IF(otam_logits(h, h->mod_out, h->protos, Q, way, T, single_direct, logits, h->dists, h->cum, st));
     h->last_S = S; h->last_Q = Q; h->last_T = T; h->last_way = way; h->last_rows = rows;
+    h->last_sup = sup; h->last_tgt = tgt;
     return 0;
 }
 
@@ -696,28 +698,56 @@ int check_episode(fsar_handle* h, const fsar_episode* ep) {
     return 0;
 }
 
-int episode_forward_dev(fsar_handle* h, const fsar_episode* ep, float* logits, float* class_logits, cudaStream_t st) {
-    const int T = ep->n_frames;
-    RET_IF(vit_encode_segments(h, ep->support_frames, ep->n_support * T, ep->target_frames, ep->n_target * T, h->feats, st));
-    return head_forward(h, ep->support_labels, ep->real_support_labels, ep->n_support, ep->n_target, T, ep->way,
-                        ep->merge_before, ep->single_direct, logits, class_logits, st);
+int check_batch(fsar_handle* h, const fsar_episode* eps, int n) {
+    if (eps == nullptr || n < 1) return fail(h, FSAR_E_INVALID, "episodes: NULL array or n_episodes < 1");
+    if (n > h->cfg.max_batch) return fail(h, FSAR_E_STATE, "%d episodes exceed max_batch %d", n, h->cfg.max_batch);
+    for (int i = 0; i < n; ++i) RET_IF(check_episode(h, &eps[i]));
+    return 0;
+}
+
+// n episodes with DEVICE pointers: one frame-encoder sweep over all their frames, then the head per episode.
+// logits: concatenated [n_target_i * way_i]; class_logits (or NULL): concatenated [(S_i + Q_i) * n_train].
+int episodes_forward_dev(fsar_handle* h, const fsar_episode* eps, int n, float* logits, float* class_logits,
+                         cudaStream_t st) {
+    const int E = h->cfg.embed_dim;
+    std::vector<const float*> ptrs;
+    std::vector<int> counts;
+    for (int i = 0; i < n; ++i) {
+        ptrs.push_back(eps[i].support_frames); counts.push_back(eps[i].n_support * eps[i].n_frames);
+        ptrs.push_back(eps[i].target_frames);  counts.push_back(eps[i].n_target * eps[i].n_frames);
+    }
+    RET_IF(vit_encode_segments(h, ptrs.data(), counts.data(), (int)ptrs.size(), h->feats, st));
+    size_t f_off = 0, l_off = 0, c_off = 0;
+    for (int i = 0; i < n; ++i) {
+        const fsar_episode& ep = eps[i];
+        const int T = ep.n_frames;
+        const float* sup = h->feats + f_off;
+        const float* tgt = sup + (size_t)ep.n_support * T * E;
+        RET_IF(head_forward(h, sup, tgt, ep.support_labels, ep.real_support_labels, ep.n_support, ep.n_target, T, ep.way,
+                            ep.merge_before, ep.single_direct, logits + l_off,
+                            class_logits ? class_logits + c_off : nullptr, st));
+        f_off += (size_t)(ep.n_support + ep.n_target) * T * E;
+        l_off += (size_t)ep.n_target * ep.way;
+        c_off += (size_t)(ep.n_support + ep.n_target) * h->n_text_train;
+    }
+    return 0;
 }
 
 int ensure_host_path(fsar_handle* h) {
     if (h->copy_stream != nullptr) return 0;
     const fsar_config& c = h->cfg;
     const size_t frame_elems = (size_t)3 * c.image_size * c.image_size;
-    const size_t V = c.max_videos;
+    const size_t V = c.max_videos, B = c.max_batch;
     CU_OK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CU_OK(h, cudaStreamCreateWithFlags(&h->compute_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
         HostSlot& s = h->slot[i];
-        RET_IF(dalloc(h, &s.frames_dev, V * c.max_tokens * frame_elems));
-        RET_IF(dalloc(h, &s.labels_dev, 2 * V));
-        RET_IF(dalloc(h, &s.logits_dev, V * V));
-        RET_IF(dalloc(h, &s.clogits_dev, V * (size_t)c.max_classes));
-        CU_OK(h, cudaMallocHost(&s.logits_pin, sizeof(float) * V * V));
-        CU_OK(h, cudaMallocHost(&s.clogits_pin, sizeof(float) * V * c.max_classes));
+        RET_IF(dalloc(h, &s.frames_dev, B * V * c.max_tokens * frame_elems));
+        RET_IF(dalloc(h, &s.labels_dev, B * 2 * V));
+        RET_IF(dalloc(h, &s.logits_dev, B * V * V));
+        RET_IF(dalloc(h, &s.clogits_dev, B * V * (size_t)c.max_classes));
+        CU_OK(h, cudaMallocHost(&s.logits_pin, sizeof(float) * B * V * V));
+        CU_OK(h, cudaMallocHost(&s.clogits_pin, sizeof(float) * B * V * c.max_classes));
         CU_OK(h, cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
         CU_OK(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     }
@@ -752,6 +782,8 @@ int fsar_create(const fsar_config* cfg, fsar_handle** out) {
         return fail(nullptr, FSAR_E_INVALID, "width %d must be a multiple of 128, <= 1024 and equal heads * 64 (heads %d)", c.width, c.heads);
     if (c.embed_dim % 128 != 0 || c.embed_dim > 1024 || c.mod_heads * c.mod_dim_head <= 0 || c.mod_depth < 1 || c.layers < 1)
         return fail(nullptr, FSAR_E_INVALID, "unsupported head geometry (embed_dim %d, mod heads %d x %d, depth %d)", c.embed_dim, c.mod_heads, c.mod_dim_head, c.mod_depth);
+    if (c.max_batch < 1 || c.max_batch > 64)
+        return fail(nullptr, FSAR_E_INVALID, "max_batch %d must be in [1, 64]", c.max_batch);
     if (c.max_frames < 1 || c.max_videos < 2 || c.max_tokens < 1 || c.max_tokens > OTAM_MAX_T || c.max_classes < 1)
         return fail(nullptr, FSAR_E_INVALID, "bad capacities (max_frames %d, max_videos %d, max_tokens %d <= %d, max_classes %d)", c.max_frames, c.max_videos, c.max_tokens, OTAM_MAX_T, c.max_classes);
     int ndev = 0;
@@ -886,7 +918,7 @@ int fsar_vit_forward(fsar_handle* h, const float* frames_dev, int n_frames, floa
     if (h == nullptr || frames_dev == nullptr || feats_dev == nullptr || n_frames < 1)
         return fail(h, FSAR_E_INVALID, "fsar_vit_forward: bad argument");
     if (!ready(h, false)) return fail(h, FSAR_E_STATE, "%d weights have not been set (first: %s)", fsar_missing_weights(h), fsar_missing_weight(h, 0));
-    return vit_encode_segments(h, frames_dev, n_frames, nullptr, 0, feats_dev, (cudaStream_t)stream);
+    return vit_encode_segments(h, &frames_dev, &n_frames, 1, feats_dev, (cudaStream_t)stream);
 }
 
 int fsar_modulate(fsar_handle* h, const float* x_dev, int n_seq, int n_tok, float* out_dev, void* stream) {
@@ -906,56 +938,75 @@ int fsar_otam_logits(fsar_handle* h, const float* q_dev, const float* protos_dev
     return otam_logits(h, q_dev, protos_dev, Q, way, T, single_direct, logits_dev, dists_dev, cum_dev, (cudaStream_t)stream);
 }
 
-int fsar_episode_forward(fsar_handle* h, const fsar_episode* ep, float* logits_dev, float* class_logits_dev, void* stream) {
-    if (h == nullptr || logits_dev == nullptr) return fail(h, FSAR_E_INVALID, "fsar_episode_forward: NULL argument");
-    RET_IF(check_episode(h, ep));
-    return episode_forward_dev(h, ep, logits_dev, class_logits_dev, (cudaStream_t)stream);
+int fsar_episodes_forward(fsar_handle* h, const fsar_episode* eps, int n_episodes, float* logits_dev,
+                          float* class_logits_dev, void* stream) {
+    if (h == nullptr || logits_dev == nullptr) return fail(h, FSAR_E_INVALID, "fsar_episodes_forward: NULL argument");
+    RET_IF(check_batch(h, eps, n_episodes));
+    return episodes_forward_dev(h, eps, n_episodes, logits_dev, class_logits_dev, (cudaStream_t)stream);
 }
 
-int fsar_episode_submit_host(fsar_handle* h, int slot, const fsar_episode* ep) {
-    if (h == nullptr || slot < 0 || slot > 1) return fail(h, FSAR_E_INVALID, "fsar_episode_submit_host: bad argument");
-    RET_IF(check_episode(h, ep));
+int fsar_episode_forward(fsar_handle* h, const fsar_episode* ep, float* logits_dev, float* class_logits_dev, void* stream) {
+    return fsar_episodes_forward(h, ep, 1, logits_dev, class_logits_dev, stream);
+}
+
+int fsar_episodes_submit_host(fsar_handle* h, int slot, const fsar_episode* eps, int n_episodes) {
+    if (h == nullptr || slot < 0 || slot > 1) return fail(h, FSAR_E_INVALID, "fsar_episodes_submit_host: bad argument");
+    RET_IF(check_batch(h, eps, n_episodes));
     CU_OK(h, cudaSetDevice(h->cfg.device));
     RET_IF(ensure_host_path(h));
     HostSlot& s = h->slot[slot];
-    if (s.busy) return fail(h, FSAR_E_STATE, "slot %d still holds an uncollected episode", slot);
+    if (s.busy) return fail(h, FSAR_E_STATE, "slot %d still holds uncollected episodes", slot);
     const fsar_config& c = h->cfg;
     const size_t frame_elems = (size_t)3 * c.image_size * c.image_size;
-    const int S = ep->n_support, Q = ep->n_target, T = ep->n_frames;
-    // the slot's buffers are free once its previous episode finished (done event of that slot was waited in collect)
-    CU_OK(h, cudaMemcpyAsync(s.frames_dev, ep->support_frames, sizeof(float) * S * T * frame_elems, cudaMemcpyHostToDevice, h->copy_stream));
-    CU_OK(h, cudaMemcpyAsync(s.frames_dev + (size_t)S * T * frame_elems, ep->target_frames, sizeof(float) * Q * T * frame_elems, cudaMemcpyHostToDevice, h->copy_stream));
-    CU_OK(h, cudaMemcpyAsync(s.labels_dev, ep->support_labels, sizeof(float) * S, cudaMemcpyHostToDevice, h->copy_stream));
-    CU_OK(h, cudaMemcpyAsync(s.labels_dev + c.max_videos, ep->real_support_labels, sizeof(float) * S, cudaMemcpyHostToDevice, h->copy_stream));
+    // the slot's buffers are free: its previous batch was collected (done event waited in collect)
+    std::vector<fsar_episode> dev(eps, eps + n_episodes);
+    size_t f_off = 0, n_logits = 0, n_clogits = 0;
+    for (int i = 0; i < n_episodes; ++i) {
+        const fsar_episode& ep = eps[i];
+        const size_t ns = (size_t)ep.n_support * ep.n_frames * frame_elems, nt = (size_t)ep.n_target * ep.n_frames * frame_elems;
+        float* lab = s.labels_dev + (size_t)i * 2 * c.max_videos;
+        CU_OK(h, cudaMemcpyAsync(s.frames_dev + f_off, ep.support_frames, sizeof(float) * ns, cudaMemcpyHostToDevice, h->copy_stream));
+        CU_OK(h, cudaMemcpyAsync(s.frames_dev + f_off + ns, ep.target_frames, sizeof(float) * nt, cudaMemcpyHostToDevice, h->copy_stream));
+        CU_OK(h, cudaMemcpyAsync(lab, ep.support_labels, sizeof(float) * ep.n_support, cudaMemcpyHostToDevice, h->copy_stream));
+        CU_OK(h, cudaMemcpyAsync(lab + c.max_videos, ep.real_support_labels, sizeof(float) * ep.n_support, cudaMemcpyHostToDevice, h->copy_stream));
+        dev[i].support_frames = s.frames_dev + f_off;
+        dev[i].target_frames = s.frames_dev + f_off + ns;
+        dev[i].support_labels = lab;
+        dev[i].real_support_labels = lab + c.max_videos;
+        f_off += ns + nt;
+        n_logits += (size_t)ep.n_target * ep.way;
+        n_clogits += (size_t)(ep.n_support + ep.n_target) * h->n_text_train;
+    }
     CU_OK(h, cudaEventRecord(s.copied, h->copy_stream));
     CU_OK(h, cudaStreamWaitEvent(h->compute_stream, s.copied, 0));
-    fsar_episode dev = *ep;
-    dev.support_frames = s.frames_dev;
-    dev.target_frames = s.frames_dev + (size_t)S * T * frame_elems;
-    dev.support_labels = s.labels_dev;
-    dev.real_support_labels = s.labels_dev + c.max_videos;
-    RET_IF(episode_forward_dev(h, &dev, s.logits_dev, s.clogits_dev, h->compute_stream));
-    CU_OK(h, cudaMemcpyAsync(s.logits_pin, s.logits_dev, sizeof(float) * Q * ep->way, cudaMemcpyDeviceToHost, h->compute_stream));
-    CU_OK(h, cudaMemcpyAsync(s.clogits_pin, s.clogits_dev, sizeof(float) * (S + Q) * h->n_text_train, cudaMemcpyDeviceToHost, h->compute_stream));
+    RET_IF(episodes_forward_dev(h, dev.data(), n_episodes, s.logits_dev, s.clogits_dev, h->compute_stream));
+    CU_OK(h, cudaMemcpyAsync(s.logits_pin, s.logits_dev, sizeof(float) * n_logits, cudaMemcpyDeviceToHost, h->compute_stream));
+    CU_OK(h, cudaMemcpyAsync(s.clogits_pin, s.clogits_dev, sizeof(float) * n_clogits, cudaMemcpyDeviceToHost, h->compute_stream));
     CU_OK(h, cudaEventRecord(s.done, h->compute_stream));
-    s.n_support = S; s.n_target = Q; s.way = ep->way; s.busy = 1;
+    s.n_logits = n_logits; s.n_clogits = n_clogits; s.busy = 1;
     return 0;
 }
 
-int fsar_episode_collect_host(fsar_handle* h, int slot, float* logits_host, float* class_logits_host) {
-    if (h == nullptr || slot < 0 || slot > 1) return fail(h, FSAR_E_INVALID, "fsar_episode_collect_host: bad argument");
+int fsar_episodes_collect_host(fsar_handle* h, int slot, float* logits_host, float* class_logits_host) {
+    if (h == nullptr || slot < 0 || slot > 1) return fail(h, FSAR_E_INVALID, "fsar_episodes_collect_host: bad argument");
     HostSlot& s = h->slot[slot];
     if (!s.busy) return fail(h, FSAR_E_STATE, "slot %d holds no submitted episode", slot);
     CU_OK(h, cudaEventSynchronize(s.done));
     s.busy = 0;
-    if (logits_host) memcpy(logits_host, s.logits_pin, sizeof(float) * s.n_target * s.way);
-    if (class_logits_host) memcpy(class_logits_host, s.clogits_pin, sizeof(float) * (s.n_support + s.n_target) * h->n_text_train);
+    if (logits_host) memcpy(logits_host, s.logits_pin, sizeof(float) * s.n_logits);
+    if (class_logits_host) memcpy(class_logits_host, s.clogits_pin, sizeof(float) * s.n_clogits);
     return 0;
 }
 
+int fsar_episode_submit_host(fsar_handle* h, int slot, const fsar_episode* ep) { return fsar_episodes_submit_host(h, slot, ep, 1); }
+
+int fsar_episode_collect_host(fsar_handle* h, int slot, float* logits_host, float* class_logits_host) {
+    return fsar_episodes_collect_host(h, slot, logits_host, class_logits_host);
+}
+
 int fsar_episode_forward_host(fsar_handle* h, const fsar_episode* ep, float* logits_host, float* class_logits_host) {
-    RET_IF(fsar_episode_submit_host(h, 0, ep));
-    return fsar_episode_collect_host(h, 0, logits_host, class_logits_host);
+    RET_IF(fsar_episodes_submit_host(h, 0, ep, 1));
+    return fsar_episodes_collect_host(h, 0, logits_host, class_logits_host);
 }
 
 int64_t fsar_peek(fsar_handle* h, const char* name, void* dst_host, int64_t numel, void* stream) {
@@ -965,8 +1016,8 @@ int64_t fsar_peek(fsar_handle* h, const char* name, void* dst_host, int64_t nume
     int64_t avail = 0;
     size_t esz = sizeof(float);
     const std::string n(name);
-    if (n == "support_feats") { src = h->feats; avail = (int64_t)S * T * E; }
-    else if (n == "target_feats") { src = h->feats + (size_t)S * T * E; avail = (int64_t)Q * T * E; }
+    if (n == "support_feats") { src = h->last_sup; avail = (int64_t)S * T * E; }
+    else if (n == "target_feats") { src = h->last_tgt; avail = (int64_t)Q * T * E; }
     else if (n == "mod_out") { src = h->mod_out; avail = (int64_t)h->last_rows * E; }
     else if (n == "protos") { src = h->protos; avail = (int64_t)way * T * E; }
     else if (n == "dists") { src = h->dists; avail = (int64_t)Q * way * T * T; }

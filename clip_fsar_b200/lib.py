@@ -21,6 +21,7 @@ SYMBOLS = [
     "fsar_version", "fsar_class_name", "fsar_create", "fsar_destroy", "fsar_last_error", "fsar_set_weight",
     "fsar_missing_weights", "fsar_missing_weight", "fsar_vit_forward", "fsar_modulate", "fsar_otam_logits",
     "fsar_episode_forward", "fsar_episode_forward_host", "fsar_episode_submit_host", "fsar_episode_collect_host",
+    "fsar_episodes_forward", "fsar_episodes_submit_host", "fsar_episodes_collect_host",
     "fsar_peek", "fsar_operand_dtype", "fsar_op_layernorm", "fsar_op_gemm", "fsar_op_attention", "fsar_op_f32_to_16",
     "fsar_launch_count", "fsar_profile_begin", "fsar_profile_end",
 ]
@@ -37,7 +38,8 @@ class FsarConfig(Structure):
         ("image_size", c_int32), ("patch_size", c_int32), ("width", c_int32), ("layers", c_int32),
         ("heads", c_int32), ("embed_dim", c_int32), ("mod_heads", c_int32), ("mod_dim_head", c_int32),
         ("mod_mlp_dim", c_int32), ("mod_depth", c_int32), ("max_frames", c_int32), ("max_videos", c_int32),
-        ("max_tokens", c_int32), ("max_classes", c_int32), ("otam_lambda", c_float), ("device", c_int32),
+        ("max_tokens", c_int32), ("max_classes", c_int32), ("max_batch", c_int32), ("otam_lambda", c_float),
+        ("device", c_int32),
     ]
 
 
@@ -91,6 +93,9 @@ def load_library(path=None):
     lib.fsar_episode_forward_host.argtypes = [H, POINTER(FsarEpisode), c_void_p, c_void_p]
     lib.fsar_episode_submit_host.argtypes = [H, c_int, POINTER(FsarEpisode)]
     lib.fsar_episode_collect_host.argtypes = [H, c_int, c_void_p, c_void_p]
+    lib.fsar_episodes_forward.argtypes = [H, POINTER(FsarEpisode), c_int, c_void_p, c_void_p, c_void_p]
+    lib.fsar_episodes_submit_host.argtypes = [H, c_int, POINTER(FsarEpisode), c_int]
+    lib.fsar_episodes_collect_host.argtypes = [H, c_int, c_void_p, c_void_p]
     lib.fsar_peek.argtypes = [H, c_char_p, c_void_p, c_int64, c_void_p]
     lib.fsar_peek.restype = c_int64
     lib.fsar_operand_dtype.restype = c_int
@@ -107,7 +112,8 @@ def load_library(path=None):
     return lib
 
 
-def geometry(backbone_name, num_frames=8, max_frames=None, max_videos=10, max_classes=128, mod_depth=1, device=0):
+def geometry(backbone_name, num_frames=8, max_frames=None, max_videos=10, max_classes=128, mod_depth=1, device=0,
+             max_batch=1):
     """fsar_config for the CLIP visual towers CNN_OTAM_CLIPFSAR can be built on (few_shot.py:2705-2713).
     ViT-L/14 is an extension: the reference head has no branch for it (SURVEY.md headline finding 2)."""
     table = {
@@ -120,7 +126,8 @@ def geometry(backbone_name, num_frames=8, max_frames=None, max_videos=10, max_cl
     g = dict(table[backbone_name])
     g.update(mod_heads=8, mod_dim_head=g["embed_dim"] // 8, mod_mlp_dim=2048, mod_depth=int(mod_depth),
              max_frames=int(max_frames or min(max_videos * num_frames, 384)), max_videos=int(max_videos),
-             max_tokens=int(num_frames), max_classes=int(max_classes), otam_lambda=0.5, device=int(device))
+             max_tokens=int(num_frames), max_classes=int(max_classes), max_batch=int(max_batch), otam_lambda=0.5,
+             device=int(device))
     return g
 
 
@@ -132,6 +139,8 @@ class Engine:
 
         self._torch = torch
         self.lib = load_library()
+        cfg = dict(cfg)
+        cfg.setdefault("max_batch", 1)
         self.cfg = FsarConfig(**cfg)
         self._h = c_void_p()
         rc = self.lib.fsar_create(byref(self.cfg), byref(self._h))
@@ -255,6 +264,38 @@ class Engine:
                                                   c_void_p(cl.data_ptr()) if cl is not None else None,
                                                   self._stream()))
         return logits, cl
+
+    def episodes_forward(self, episodes, n_frames, way, merge_before=False, single_direct=False, n_train_classes=None,
+                         want_class_logits=True):
+        """Throughput form: `episodes` is a list of (support, target, support_labels, real_support_labels) DEVICE
+        tensors with the same way / shot / n_frames. One ViT sweep over all frames (passes of cfg.max_frames frames),
+        head per episode. Returns (logits [n, Q, way], class_logits [n, S + Q, n_train] or None)."""
+        torch = self._torch
+        n = len(episodes)
+        arr = (FsarEpisode * n)()
+        for i, (sup, tgt, sl, rl) in enumerate(episodes):
+            for name, t in (("support_set", sup), ("target_set", tgt), ("support_labels", sl), ("real_support_labels", rl)):
+                self._f32(t, name)
+            arr[i], S, Q = self._episode(sup, tgt, sl, rl, n_frames, way, merge_before, single_direct)
+        logits = torch.empty((n, Q, way), dtype=torch.float32, device=self.device)
+        cl = torch.empty((n, S + Q, int(n_train_classes)), dtype=torch.float32, device=self.device) if want_class_logits else None
+        self._check(self.lib.fsar_episodes_forward(self._h, arr, n, c_void_p(logits.data_ptr()),
+                                                   c_void_p(cl.data_ptr()) if cl is not None else None, self._stream()))
+        return logits, cl
+
+    def episodes_submit_host(self, slot, episodes, n_frames, way, merge_before=False, single_direct=False):
+        """`episodes`: list of (support, target, support_labels, real_support_labels) HOST (ideally pinned) tensors."""
+        n = len(episodes)
+        arr = (FsarEpisode * n)()
+        for i, (sup, tgt, sl, rl) in enumerate(episodes):
+            arr[i], S, Q = self._host_episode(sup, tgt, sl, rl, n_frames, way, merge_before, single_direct)
+        self._check(self.lib.fsar_episodes_submit_host(self._h, slot, arr, n))
+        return n, S, Q
+
+    def episodes_collect_host(self, slot, logits_out, class_logits_out=None):
+        self._check(self.lib.fsar_episodes_collect_host(
+            self._h, slot, c_void_p(logits_out.data_ptr()),
+            c_void_p(class_logits_out.data_ptr()) if class_logits_out is not None else None))
 
     def _host_episode(self, support, target, support_labels, real_support_labels, n_frames, way, merge_before,
                       single_direct):

@@ -56,6 +56,7 @@ typedef struct fsar_config {
     int32_t max_videos;      /* capacity: support + query videos of one episode */
     int32_t max_tokens;      /* capacity: DATA.NUM_INPUT_FRAMES (T <= 32) */
     int32_t max_classes;     /* capacity: rows of text_features_{train,test} */
+    int32_t max_batch;       /* capacity: episodes per fsar_episodes_* call (1 = single-episode use) */
     float otam_lambda;       /* 0.5, OTAM_cum_dist_v2 default (few_shot.py:2657) */
     int32_t device;          /* CUDA device ordinal */
 } fsar_config;
@@ -125,6 +126,16 @@ int fsar_otam_logits(fsar_handle* h, const float* q_dev, const float* protos_dev
  * logits_dev [n_target, way]; class_logits_dev [n_support + n_target, n_train_classes] (may be NULL). */
 int fsar_episode_forward(fsar_handle* h, const fsar_episode* ep_dev, float* logits_dev, float* class_logits_dev,
                          void* stream);
+
+/* Throughput form of the same forward: n_episodes independent episodes (a host array of fsar_episode holding DEVICE
+ * pointers) in one call. All their frames are encoded in ViT passes of cfg.max_frames frames irrespective of episode
+ * boundaries — with max_frames = 96 every ViT-B/16 GEMM runs whole waves of 256 x 256 tiles on 148 SMs — and the head
+ * runs per episode. Results are concatenated: logits_dev [sum_i n_target_i * way_i], class_logits_dev (may be NULL)
+ * [sum_i (n_support_i + n_target_i) * n_train_classes]. Same math per episode as fsar_episode_forward. */
+int fsar_episodes_forward(fsar_handle* h, const fsar_episode* eps_dev, int n_episodes, float* logits_dev,
+                          float* class_logits_dev, void* stream);
+int fsar_episodes_submit_host(fsar_handle* h, int slot, const fsar_episode* eps_host, int n_episodes);
+int fsar_episodes_collect_host(fsar_handle* h, int slot, float* logits_host, float* class_logits_host);
 
 /* Same, with HOST buffers: host->device copies of the frames/labels and the device->host copy of the
  * results happen inside the call (pinned host memory makes them asynchronous up to the final sync).

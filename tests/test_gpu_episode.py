@@ -79,7 +79,7 @@ def test_episode_matches_16bit_emulating_oracle_tightly(lib, name):
     out = O.episode_forward(sd, g, tt, te, task, meta["T"], meta["merge_before"], meta["single_direct"],
                             operand_dtype=e.operand_dtype)
     S, T, E = meta["way"] * meta["shot"], meta["T"], g["embed_dim"]
-    assert rel_l2(e.peek("support_feats", (S, T, E)), out["support_feats"]) < 1e-3
+    assert rel_l2(e.peek("support_feats", (S, T, E)), out["support_feats"]) < 1.5e-3      # tanh.approx vs torch.tanh
     assert rel_max(logits, out["logits"]) < 1e-3
     assert torch.equal(e.peek("class_index", (S,), torch.int32).long(), out["class_index"])
     e.close()
@@ -131,6 +131,39 @@ def test_pipelined_submit_collect(lib):
         assert torch.equal(o, ref.cpu())
     with pytest.raises(lib.FsarError):
         e.episode_collect_host(0, outs[0])                                     # nothing submitted
+    e.close()
+
+
+def test_batched_episodes_equal_single_episode_calls(lib):
+    """fsar_episodes_forward regroups the frames of several episodes into ViT passes that ignore episode boundaries;
+    per episode the result must be what fsar_episode_forward gives (same kernels on the same rows: bit equal for the
+    head, and the ViT rows only move between GEMM tiles)."""
+    from clip_fsar_b200 import synth
+    meta, _ = load_golden("tiny_5w1s")
+    g, sd, tt, te, _ = regenerate(meta)
+    n_vid = meta["way"] * (meta["shot"] + 1)
+    e = lib.Engine(**dict(g, max_frames=96, max_videos=n_vid, max_tokens=meta["T"], max_classes=128, max_batch=6,
+                          otam_lambda=0.5, device=0))
+    e.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    e.set_weight("text_features_train", torch.from_numpy(tt))
+    e.set_weight("text_features_test", torch.from_numpy(te))
+    keys = ("support_set", "target_set", "support_labels", "real_support_labels")
+    eps_np = [synth.synth_episode(5, 1, 1, 8, g["image_size"], 24, 2000 + i) for i in range(6)]
+    eps = [[torch.from_numpy(ep[k]).to(DEV) for k in keys] for ep in eps_np]
+    singles = [e.episode_forward(*ep, 8, 5, n_train_classes=64) for ep in eps]
+    logits, cl = e.episodes_forward(eps, 8, 5, n_train_classes=64)
+    for i in range(6):
+        assert rel_max(logits[i], singles[i][0]) < 2e-4 and rel_max(cl[i], singles[i][1]) < 2e-4
+    # host entry points, two slots
+    pinned = [[torch.from_numpy(ep[k]).pin_memory() for k in keys] for ep in eps_np]
+    e.episodes_submit_host(0, pinned[:3], 8, 5)
+    e.episodes_submit_host(1, pinned[3:], 8, 5)
+    a, b = torch.empty(3, 5, 5), torch.empty(3, 5, 5)
+    e.episodes_collect_host(0, a)
+    e.episodes_collect_host(1, b)
+    assert rel_max(torch.cat([a, b]), logits.cpu()) < 2e-4
+    with pytest.raises(lib.FsarError):
+        e.episodes_forward(eps + eps, 8, 5, n_train_classes=64)             # 12 > max_batch
     e.close()
 
 
