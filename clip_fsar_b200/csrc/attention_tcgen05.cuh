@@ -17,7 +17,8 @@
 //   epilogue: tcgen05.ld O -> * 1/rowsum -> fp16 -> one 128-byte row per thread to global
 // Two row groups g (query rows 0-127 and 128-255) own TMEM columns [0,256) and [256,512) and 4 warps each, so the
 // tensor pipe works for one group while the other is in its softmax.
-// Warp roles (384 threads): 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-7 softmax group 0, 8-11 group 1.
+// Warp roles (384 threads): 0 TMA producer, 1 / 3 MMA issuers of group 0 / 1, 2 TMEM allocator, 4-7 softmax group 0,
+// 8-11 softmax group 1.
 #pragma once
 #include "gemm_tcgen05.cuh"  // pack2<>
 #include "ptx.cuh"
@@ -44,6 +45,7 @@ struct Att5Params {
     int n_mtiles;    // 1 or 2 query tiles of 128 rows
     float scale_log2e;
     void* out;       // [n_frames * L, D] 16-bit
+    int reverse;     // walk the (frame, head) items last-to-first (L2 reuse of the QKV rows written last)
 };
 
 template <typename T16>
@@ -72,7 +74,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&empty_bar[i], p.n_mtiles);   // one commit per row group
             mbar_init(&s_full[i], 1);
             mbar_init(&p_full[i], 4);
             mbar_init(&o_full[i], 1);
@@ -96,7 +98,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
             const int s = i & 1;
             const uint32_t ph = (i >> 1) & 1;
-            const int frame = item / p.heads, head = item - frame * p.heads;
+            const int it = p.reverse ? n_items - 1 - item : item;
+            const int frame = it / p.heads, head = it - frame * p.heads;
             uint8_t* st = smem + s * ATT5_STAGE_BYTES;
             mbar_wait(&empty_bar[s], ph ^ 1);
             if (elect_one()) {
@@ -108,45 +111,44 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             }
             __syncwarp();
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (warp-uniform loop, elected lane)
-        const uint32_t idesc_s = umma_idesc_f16(128, p.LK, kBf16, false, false);   // S = Q K^T, both K-major
-        const uint32_t idesc_o = umma_idesc_f16(128, 64, kBf16, false, true);      // O = P V, V is MN-major
-        constexpr uint64_t desc_hi = umma_smem_desc_hi(0, 1024, UMMA_LAYOUT_SW128);
-        const int ksteps_o = p.LK / 16;
-        int i = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
-            const int s = i & 1;
-            const uint32_t ph = (i >> 1) & 1, ip = i & 1;
-            uint8_t* st = smem + s * ATT5_STAGE_BYTES;
-            const uint32_t q_addr = smem_u32(st), k_addr = smem_u32(st + ATT5_Q_BYTES),
-                           v_addr = smem_u32(st + ATT5_Q_BYTES + ATT5_KV_BYTES);
-            mbar_wait(&full_bar[s], ph);
-            tc_fence_after();
-            for (int g = 0; g < p.n_mtiles; ++g) {
+    } else if (warp == 1 || warp == 3) {
+        // ------------------------------------------------------------ MMA issuers: warp 1 drives row group 0, warp 3
+        // row group 1, so the S -> softmax -> PV chain of one group never waits behind the other group's barriers
+        // (warp-uniform loops, one elected lane issues)
+        const int g = (warp == 1) ? 0 : 1;
+        if (g < p.n_mtiles) {
+            const uint32_t idesc_s = umma_idesc_f16(128, p.LK, kBf16, false, false);   // S = Q K^T, both K-major
+            const uint32_t idesc_o = umma_idesc_f16(128, 64, kBf16, false, true);      // O = P V, V is MN-major
+            constexpr uint64_t desc_hi = umma_smem_desc_hi(0, 1024, UMMA_LAYOUT_SW128);
+            const int ksteps_o = p.LK / 16;
+            const uint32_t d_s = tmem_base + g * 256;                 // S (fp32) and P (16-bit pairs) columns
+            const uint32_t d_o = tmem_base + g * 256 + ATT5_O_COL;
+            int i = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+                const int s = i & 1;
+                const uint32_t ph = (i >> 1) & 1, ip = i & 1;
+                uint8_t* st = smem + s * ATT5_STAGE_BYTES;
+                const uint32_t q_addr = smem_u32(st) + g * 128 * 128, k_addr = smem_u32(st + ATT5_Q_BYTES),
+                               v_addr = smem_u32(st + ATT5_Q_BYTES + ATT5_KV_BYTES);
+                mbar_wait(&full_bar[s], ph);
                 mbar_wait(&o_empty[g], ip ^ 1);   // previous item's O (aliases S columns) has been read
                 tc_fence_after();
-                const uint32_t d_s = tmem_base + g * 256;
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_f16_ss(d_s, umma_smem_desc(q_addr + g * 128 * 128 + k * 32, desc_hi),
-                                    umma_smem_desc(k_addr + k * 32, desc_hi), idesc_s, k != 0 ? 1u : 0u);
+                        umma_f16_ss(d_s, umma_smem_desc(q_addr + k * 32, desc_hi), umma_smem_desc(k_addr + k * 32, desc_hi),
+                                    idesc_s, k != 0 ? 1u : 0u);
                     umma_commit(&s_full[g]);
                 }
                 __syncwarp();
-            }
-            for (int g = 0; g < p.n_mtiles; ++g) {
                 mbar_wait(&p_full[g], ip);
                 tc_fence_after();
-                const uint32_t d_o = tmem_base + g * 256 + ATT5_O_COL;
-                const uint32_t a_p = tmem_base + g * 256;   // P: 16-bit pairs, 8 columns per 16-key k-step
                 if (elect_one()) {
                     for (int kk = 0; kk < ksteps_o; ++kk)
-                        umma_f16_ts(d_o, a_p + kk * 8, umma_smem_desc(v_addr + kk * 2048, desc_hi), idesc_o,
+                        umma_f16_ts(d_o, d_s + kk * 8, umma_smem_desc(v_addr + kk * 2048, desc_hi), idesc_o,
                                     kk != 0 ? 1u : 0u);
                     umma_commit(&o_full[g]);
-                    if (g == p.n_mtiles - 1) umma_commit(&empty_bar[s]);   // Q/K/V of this stage are no longer read
+                    umma_commit(&empty_bar[s]);   // this group no longer reads Q/K/V of the stage
                 }
                 __syncwarp();
             }
@@ -166,7 +168,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             int i = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
                 const uint32_t ip = i & 1;
-                const int frame = item / p.heads, head = item - frame * p.heads;
+                const int it = p.reverse ? n_items - 1 - item : item;
+            const int frame = it / p.heads, head = it - frame * p.heads;
                 float sum = 0.f;
                 mbar_wait(&s_full[g], ip);
                 tc_fence_after();

@@ -106,6 +106,7 @@ struct fsar_handle {
     int64_t launches = 0;
     bool profiling = false;
     size_t l2_persist_bytes = 0, l2_window_max = 0;   // L2 set-aside for the residual stream (0 = disabled)
+    bool alternate_rows = true;     // FSAR_NO_ALTERNATE=1: every kernel walks rows first-to-last (A/B testing)
     bool single_cta_gemm = false;   // FSAR_GEMM_SINGLE=1: one CTA per 128 x 256 tile instead of CTA pairs (A/B testing)
     bool legacy_attention = false;  // FSAR_LEGACY_ATTENTION=1: mma.sync attention core also for L <= 208 (A/B testing)
     std::vector<ProfRec> prof;
@@ -256,13 +257,13 @@ int launch_gemm_bn(fsar_handle* h, int epi, const CUtensorMap& ta, const CUtenso
 
 // out[M,N] (epilogue) = A16[M,K] W16[N,K]^T (+ bias); K = row pitch of both operands, N = row pitch of out.
 int gemm(fsar_handle* h, int cls, const T16* a, const T16* w, const float* bias, void* out, int M, int N, int K, int epi,
-         cudaStream_t st) {
+         cudaStream_t st, int reverse = 0) {
     if (M <= 0 || N <= 0 || K <= 0 || (N % 8) != 0 || (K % 8) != 0)
         return fail(h, FSAR_E_INVALID, "gemm: unsupported shape M=%d N=%d K=%d (need N %% 8 == 0, K %% 8 == 0)", M, N, K);
     if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out)) & 15)
         return fail(h, FSAR_E_INVALID, "gemm: operands must be 16-byte aligned");
     GemmParams p{};
-    p.M = M; p.N = N; p.K = K; p.bias = bias;
+    p.M = M; p.N = N; p.K = K; p.bias = bias; p.reverse = reverse;
     const int bn = (N >= 256) ? 256 : ((N >= 128) ? 128 : 64);
     const bool out16 = (epi == EPI_STORE16 || epi == EPI_QGELU16);
     CUtensorMap ta, tb, tc;
@@ -300,21 +301,21 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, T16* __restric
 }
 
 int layernorm(fsar_handle* h, const float* x, void* out, const float* g, const float* b, int rows, int D, bool out16,
-              bool embed, int tokens, const float* cls_emb, const float* pos, cudaStream_t st, int cls) {
+              bool embed, int tokens, const float* cls_emb, const float* pos, cudaStream_t st, int cls, int reverse = 0) {
     if ((D % 128) != 0 || D > 1024) return fail(h, FSAR_E_INVALID, "layernorm: dim %d must be a multiple of 128 and <= 1024", D);
     const int wpb = 8;
     const int grid = (rows + wpb - 1) / wpb;
     Scope s(h, st, cls, 0.0, (double)rows * D * (4.0 + (out16 ? 2.0 : 4.0)));
     if (embed)
-        layernorm_kernel<T16, false, true><<<grid, 256, 0, st>>>(x, out, g, b, rows, D, 1e-5f, tokens, cls_emb, pos);
+        layernorm_kernel<T16, false, true><<<grid, 256, 0, st>>>(x, out, g, b, rows, D, 1e-5f, tokens, cls_emb, pos, reverse);
     else if (out16)
-        layernorm_kernel<T16, true, false><<<grid, 256, 0, st>>>(x, out, g, b, rows, D, 1e-5f, tokens, nullptr, nullptr);
+        layernorm_kernel<T16, true, false><<<grid, 256, 0, st>>>(x, out, g, b, rows, D, 1e-5f, tokens, nullptr, nullptr, reverse);
     else
-        layernorm_kernel<T16, false, false><<<grid, 256, 0, st>>>(x, out, g, b, rows, D, 1e-5f, tokens, nullptr, nullptr);
+        layernorm_kernel<T16, false, false><<<grid, 256, 0, st>>>(x, out, g, b, rows, D, 1e-5f, tokens, nullptr, nullptr, reverse);
     return check_launch(h, "layernorm_kernel");
 }
 
-int attention(fsar_handle* h, const T16* qkv, int n_frames, int L, int heads, T16* out, cudaStream_t st) {
+int attention(fsar_handle* h, const T16* qkv, int n_frames, int L, int heads, T16* out, cudaStream_t st, int reverse = 0) {
     const int D = heads * ATT_HD;
     const float scale_log2e = 0.125f * 1.4426950408889634f;  // head_dim ** -0.5 * log2(e)
     Scope s(h, st, FSAR_K_ATTENTION, 4.0 * n_frames * heads * (double)L * L * ATT_HD,
@@ -329,7 +330,7 @@ int attention(fsar_handle* h, const T16* qkv, int n_frames, int L, int heads, T1
         }
         Att5Params ap{};
         ap.n_frames = n_frames; ap.L = L; ap.heads = heads; ap.D = D;
-        ap.LK = round_up(L, 16); ap.n_mtiles = (L + 127) / 128; ap.scale_log2e = scale_log2e; ap.out = out;
+        ap.LK = round_up(L, 16); ap.n_mtiles = (L + 127) / 128; ap.scale_log2e = scale_log2e; ap.out = out; ap.reverse = reverse;
         CUtensorMap tq, tkv;
         RET_IF(get_tmap(h, qkv, n_frames * L, 3 * D, 128, 64, 0, &tq));
         RET_IF(get_tmap(h, qkv, n_frames * L, 3 * D, ap.LK, 64, 0, &tkv));
@@ -532,21 +533,33 @@ int vit_encode_gathered(fsar_handle* h, int n, float* feats_out, cudaStream_t st
     RET_IF(layernorm(h, patch32, h->x32, W32(h, "backbone.ln_pre.weight"), W32(h, "backbone.ln_pre.bias"), M, D, false,
                      true, L, W32(h, "backbone.class_embedding"), W32(h, "backbone.positional_embedding"), st,
                      FSAR_K_LAYERNORM));
+    // Row direction alternates from kernel to kernel (dir ^= 1): every consumer walks the rows in the opposite order
+    // of the producer of its big input (x32 58 MB, qkv16 87 MB, h16 116 MB at 96 frames — together more than the
+    // 126 MB L2), so under LRU it starts on the rows that were written last and are still cache-resident.
+    int dir = h->alternate_rows ? 1 : 0;
+    const int flip = h->alternate_rows ? 1 : 0;
     for (int i = 0; i < c.layers; ++i) {
         const std::string pre = "backbone.transformer.resblocks." + std::to_string(i) + ".";
         RET_IF(layernorm(h, h->x32, h->ln16, W32(h, pre + "ln_1.weight"), W32(h, pre + "ln_1.bias"), M, D, true, false, L,
-                         nullptr, nullptr, st, FSAR_K_LAYERNORM));
+                         nullptr, nullptr, st, FSAR_K_LAYERNORM, dir));
+        dir ^= flip;
         RET_IF(gemm(h, FSAR_K_GEMM_QKV, h->ln16, W16(h, pre + "attn.in_proj_weight"), W32(h, pre + "attn.in_proj_bias"),
-                    h->qkv16, M, 3 * D, D, EPI_STORE16, st));
-        RET_IF(attention(h, h->qkv16, n, L, c.heads, h->att16, st));
+                    h->qkv16, M, 3 * D, D, EPI_STORE16, st, dir));
+        dir ^= flip;
+        RET_IF(attention(h, h->qkv16, n, L, c.heads, h->att16, st, dir));
+        dir ^= flip;
         RET_IF(gemm(h, FSAR_K_GEMM_OUT, h->att16, W16(h, pre + "attn.out_proj.weight"), W32(h, pre + "attn.out_proj.bias"),
-                    h->x32, M, D, D, EPI_RESID32, st));
+                    h->x32, M, D, D, EPI_RESID32, st, dir));
+        dir ^= flip;
         RET_IF(layernorm(h, h->x32, h->ln16, W32(h, pre + "ln_2.weight"), W32(h, pre + "ln_2.bias"), M, D, true, false, L,
-                         nullptr, nullptr, st, FSAR_K_LAYERNORM));
+                         nullptr, nullptr, st, FSAR_K_LAYERNORM, dir));
+        dir ^= flip;
         RET_IF(gemm(h, FSAR_K_GEMM_FC1, h->ln16, W16(h, pre + "mlp.c_fc.weight"), W32(h, pre + "mlp.c_fc.bias"), h->h16, M,
-                    4 * D, D, EPI_QGELU16, st));
+                    4 * D, D, EPI_QGELU16, st, dir));
+        dir ^= flip;
         RET_IF(gemm(h, FSAR_K_GEMM_FC2, h->h16, W16(h, pre + "mlp.c_proj.weight"), W32(h, pre + "mlp.c_proj.bias"), h->x32,
-                    M, D, 4 * D, EPI_RESID32, st));
+                    M, D, 4 * D, EPI_RESID32, st, dir));
+        dir ^= flip;
     }
     {
         const dim3 grid((n + FINAL_FPC - 1) / FINAL_FPC, (c.embed_dim + FINAL_COLS - 1) / FINAL_COLS);
@@ -804,6 +817,8 @@ int fsar_create(const fsar_config* cfg, fsar_handle** out) {
     {
         const char* e = getenv("FSAR_LEGACY_ATTENTION");
         h->legacy_attention = (e != nullptr && e[0] == '1');
+        e = getenv("FSAR_NO_ALTERNATE");
+        h->alternate_rows = !(e != nullptr && e[0] == '1');
         e = getenv("FSAR_GEMM_SINGLE");
         h->single_cta_gemm = (e != nullptr && e[0] == '1');
     }

@@ -86,8 +86,9 @@ gemm_tn_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = pair; tile < num_tiles; tile += n_pairs) {
-            const int m_blk = tile / n_tiles;
-            const int n_blk = tile - m_blk * n_tiles;
+            const int m_lin = tile / n_tiles;
+            const int n_blk = tile - m_lin * n_tiles;
+            const int m_blk = p.reverse ? m_tiles - 1 - m_lin : m_lin;
             const int a_row = m_blk * 256 + int(rank) * 128;
             const int b_row = n_blk * BN + int(rank) * (BN / 2);
             for (int kb = 0; kb < num_kb; ++kb) {
@@ -153,8 +154,9 @@ gemm_tn_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = pair; tile < num_tiles; tile += n_pairs) {
-            const int m_blk = tile / n_tiles;
-            const int n_blk = tile - m_blk * n_tiles;
+            const int m_lin = tile / n_tiles;
+            const int n_blk = tile - m_lin * n_tiles;
+            const int m_blk = p.reverse ? m_tiles - 1 - m_lin : m_lin;
             const int row0 = m_blk * 256 + int(rank) * 128 + q * 32;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();

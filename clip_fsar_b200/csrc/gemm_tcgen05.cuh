@@ -32,6 +32,8 @@ enum GemmEpilogue : int { EPI_STORE16 = 0, EPI_QGELU16 = 1, EPI_RESID32 = 2, EPI
 struct GemmParams {
     int M, N, K;        // logical sizes; K is covered in blocks of 64 (TMA zero-fills the tail)
     const float* bias;  // [N] or nullptr
+    int reverse;        // walk the row blocks last-to-first: a consumer that reads its producer's output in the opposite
+                        // order finds the most recently written rows still in L2 (LRU), see fsar.cu
 };
 
 constexpr int GEMM_BM = 128;
@@ -262,8 +264,9 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             // m-major tile order: the n-tiles of one row block run concurrently on neighbouring CTAs, so an A tile is
             // fetched from HBM once and re-used out of L2 (the weights are a few MB and stay L2-resident anyway)
-            const int m_blk = tile / n_tiles;
-            const int n_blk = tile - m_blk * n_tiles;
+            const int m_lin = tile / n_tiles;
+            const int n_blk = tile - m_lin * n_tiles;
+            const int m_blk = p.reverse ? m_tiles - 1 - m_lin : m_lin;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (elect_one()) {
@@ -327,8 +330,9 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile / n_tiles;
-            const int n_blk = tile - m_blk * n_tiles;
+            const int m_lin = tile / n_tiles;
+            const int n_blk = tile - m_lin * n_tiles;
+            const int m_blk = p.reverse ? m_tiles - 1 - m_lin : m_lin;
             const int row0 = m_blk * GEMM_BM + q * 32;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();

@@ -60,10 +60,11 @@ template <typename T16, bool OUT16, bool EMBED>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x, void* out, const float* __restrict__ gamma, const float* __restrict__ beta,
                  int rows, int D, float eps, int tokens, const float* __restrict__ cls_emb,
-                 const float* __restrict__ pos) {
+                 const float* __restrict__ pos, int reverse) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+    int row = blockIdx.x * (blockDim.x >> 5) + warp;
     if (row >= rows) return;
+    if (reverse) row = rows - 1 - row;   // blocks are scheduled in index order: last rows first
     const int nv = D >> 7;  // float4 per lane
     float4 v[8];
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
