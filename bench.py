@@ -25,6 +25,11 @@ import subprocess
 import sys
 import time
 
+# torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU-baseline legs (rank 0 only) need all host cores, and the
+# OpenMP pool is sized when torch first touches it, so lift the cap before importing torch.
+if os.environ.get("OMP_NUM_THREADS", "") in ("", "1"):
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+
 import numpy as np
 import torch
 
