@@ -274,10 +274,19 @@ def main():
     gemm_launches = sum(prof[k]["launches"] for k in gemm_classes)
     total_prof_ms = sum(v["ms"] for v in prof.values())
     achieved = gemm_flops / gemm_ms / 1e9 if gemm_ms else 0.0
+    traffic = None   # DRAM bytes per launch of the GEMM kernel from the committed ncu capture (bench cannot run ncu)
+    try:
+        nt = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["kernels"]
+        gk = [v for k, v in nt.items() if "gemm_tn_tcgen05" in k]
+        if gk:
+            traffic = sum(v["dram_bytes_per_launch"] * v["launches"] for v in gk) / sum(v["launches"] for v in gk)
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {"bound": "tensor", "kernel": "gemm_tn_tcgen05_kernel (patch/QKV/out/fc1/fc2 epilogues)",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
                 "peak_source": pk["src"] + " cuBLAS bf16, sustained (kernel timed inside a long step)",
-                "traffic": None, "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "launches_per_episode": gemm_launches / NP,
+                "traffic": traffic, "traffic_source": "profiles/ncu_traffic.json (ncu --set full, mean over the GEMM launches)",
+                "algorithmic_bytes_per_launch": None, "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "launches_per_episode": gemm_launches / NP,
                 "share_of_step": gemm_ms / total_prof_ms if total_prof_ms else None,
                 "flops_per_episode": gemm_flops / NP}
     kernels = {k: {"ms_per_episode": v["ms"] / NP, "launches_per_episode": v["launches"] / NP,
