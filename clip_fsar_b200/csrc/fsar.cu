@@ -659,13 +659,27 @@ int otam_logits(fsar_handle* h, const float* q, const float* protos, int Q, int 
 // class_logits.
 int head_forward(fsar_handle* h, const float* sup, const float* tgt, const float* support_labels,
                  const float* real_support_labels, int S, int Q, int T, int way, int merge_before, int single_direct,
-                 float* logits, float* class_logits, cudaStream_t st) {
+                 int text_mode, float text_coff, float* logits, float* class_logits, cudaStream_t st) {
     const fsar_config& c = h->cfg;
     const int E = c.embed_dim;
+    if (text_mode < 0 || text_mode > 2) return fail(h, FSAR_E_INVALID, "episode: text_mode %d not in {0, 1, 2}", text_mode);
+    if (text_mode != 0) {
+        if (way > TEXT_MAX_WAY) return fail(h, FSAR_E_INVALID, "text branches support at most %d classes", TEXT_MAX_WAY);
+        class_logits = nullptr;   // the reference returns class_logits = None in these branches (few_shot.py:2852, 2930)
+    }
     {
         Scope s(h, st, FSAR_K_HEAD_MISC, 0.0, 8.0 * S);
         class_index_kernel<<<1, 128, 0, st>>>(support_labels, S, h->cls, h->counts, way);
         RET_IF(check_launch(h, "class_index_kernel"));
+    }
+    if (text_mode == 1) {   // TRAIN.EVAL_TEXT: text probabilities only, the modulator / OTAM are not evaluated
+        Scope s(h, st, FSAR_K_HEAD_MISC, 2.0 * Q * way * E, 4.0 * ((double)Q * T * E + (double)way * E));
+        text_fusion_kernel<<<Q, 256, sizeof(float) * E, st>>>(tgt, W32(h, "text_features_test"), real_support_labels, h->cls,
+                                                              h->counts, S, T, E, way, W32(h, "scale"), 1, 0.f, nullptr, logits);
+        RET_IF(check_launch(h, "text_fusion_kernel"));
+        h->last_S = S; h->last_Q = Q; h->last_T = T; h->last_way = way; h->last_rows = 0;
+        h->last_sup = sup; h->last_tgt = tgt;
+        return 0;
     }
     if (class_logits != nullptr) {
         if (!find_w(h, "text_features_train")->set) return fail(h, FSAR_E_STATE, "text_features_train has not been set");
@@ -693,6 +707,13 @@ int head_forward(fsar_handle* h, const float* sup, const float* tgt, const float
         RET_IF(check_launch(h, "prototype_kernel"));
     }
     RET_IF(otam_logits(h, h->mod_out, h->protos, Q, way, T, single_direct, logits, h->dists, h->cum, st));
+    if (text_mode == 2) {   // TRAIN.COMBINE: geometric fusion of text and visual probabilities overwrites the logits
+        Scope s(h, st, FSAR_K_HEAD_MISC, 2.0 * Q * way * E, 4.0 * ((double)Q * T * E + (double)way * E));
+        text_fusion_kernel<<<Q, 256, sizeof(float) * E, st>>>(tgt, W32(h, "text_features_test"), real_support_labels, h->cls,
+                                                              h->counts, S, T, E, way, W32(h, "scale"), 2, text_coff, h->cum,
+                                                              logits);
+        RET_IF(check_launch(h, "text_fusion_kernel"));
+    }
     h->last_S = S; h->last_Q = Q; h->last_T = T; h->last_way = way; h->last_rows = rows;
     h->last_sup = sup; h->last_tgt = tgt;
     return 0;
@@ -737,7 +758,7 @@ int episodes_forward_dev(fsar_handle* h, const fsar_episode* eps, int n, float* 
         const float* sup = h->feats + f_off;
         const float* tgt = sup + (size_t)ep.n_support * T * E;
         RET_IF(head_forward(h, sup, tgt, ep.support_labels, ep.real_support_labels, ep.n_support, ep.n_target, T, ep.way,
-                            ep.merge_before, ep.single_direct, logits + l_off,
+                            ep.merge_before, ep.single_direct, ep.text_mode, ep.text_coff, logits + l_off,
                             class_logits ? class_logits + c_off : nullptr, st));
         f_off += (size_t)(ep.n_support + ep.n_target) * T * E;
         l_off += (size_t)ep.n_target * ep.way;
@@ -1022,6 +1043,17 @@ int fsar_episode_collect_host(fsar_handle* h, int slot, float* logits_host, floa
 int fsar_episode_forward_host(fsar_handle* h, const fsar_episode* ep, float* logits_host, float* class_logits_host) {
     RET_IF(fsar_episodes_submit_host(h, 0, ep, 1));
     return fsar_episodes_collect_host(h, 0, logits_host, class_logits_host);
+}
+
+int fsar_metrics_update(fsar_handle* h, const float* logits_dev, const float* target_labels_dev, int Q, int way,
+                        int64_t* counters_dev, int64_t* per_class_dev, void* stream) {
+    if (h == nullptr || logits_dev == nullptr || target_labels_dev == nullptr || counters_dev == nullptr || Q < 1 || way < 1)
+        return fail(h, FSAR_E_INVALID, "fsar_metrics_update: bad argument");
+    Scope s(h, (cudaStream_t)stream, FSAR_K_HEAD_MISC, 0.0, 4.0 * Q * (way + 1));
+    metrics_kernel<<<(Q + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        logits_dev, target_labels_dev, Q, way, reinterpret_cast<unsigned long long*>(counters_dev),
+        reinterpret_cast<unsigned long long*>(per_class_dev));
+    return check_launch(h, "metrics_kernel");
 }
 
 int64_t fsar_peek(fsar_handle* h, const char* name, void* dst_host, int64_t numel, void* stream) {

@@ -291,6 +291,108 @@ prototype_kernel(const float* __restrict__ mod_out, int q_rows, int n_sup_seq, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// Caller-side metrics of the episodic eval loop (runs/test_net_few_shot.py:111, 147-160; utils/metrics.py:100-138) as one
+// device kernel with deferred host read: per query top-1 correctness (first maximum wins, like torch.topk) and the
+// cross-entropy against target_labels, accumulated into int64 counters
+//   counters[0] += n_correct, counters[1] += Q, counters[2] += sum_q round(CE_q * 1e6)
+// plus optional per-class hit / count tables. Integer atomics: the result does not depend on the order of arrival.
+__global__ void metrics_kernel(const float* __restrict__ logits /*[Q,way]*/, const float* __restrict__ target_labels,
+                               int Q, int way, unsigned long long* __restrict__ counters,
+                               unsigned long long* __restrict__ per_class /*[2*way] hits | counts, or null*/) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    const float* row = logits + (size_t)q * way;
+    float mx = row[0];
+    int arg = 0;
+    for (int c = 1; c < way; ++c)
+        if (row[c] > mx) { mx = row[c]; arg = c; }
+    float sum = 0.f;
+    for (int c = 0; c < way; ++c) sum += expf(row[c] - mx);
+    const int tgt = (int)((long long)target_labels[q]);
+    const bool in_range = tgt >= 0 && tgt < way;
+    const float ce = in_range ? (logf(sum) + mx - row[tgt]) : 0.f;
+    const bool hit = in_range && arg == tgt;
+    atomicAdd(&counters[0], hit ? 1ull : 0ull);
+    atomicAdd(&counters[1], 1ull);
+    atomicAdd(&counters[2], (unsigned long long)llrintf(ce * 1.0e6f));
+    if (per_class != nullptr && in_range) {
+        atomicAdd(&per_class[tgt], hit ? 1ull : 0ull);
+        atomicAdd(&per_class[way + tgt], 1ull);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Text branches of the eval forward (few_shot.py:2835-2930). One CTA per query video.
+//   p_text[q, c] = softmax_c( scale * <img_q / |img_q|, txt_c / |txt_c|> )                      (2841-2849 / 2862-2870)
+//     img_q = mean_T(target_features[q]) (raw ViT features), txt_c = mean over the shots of class c of
+//     text_features_test[real_support_labels[s]]
+//   mode 1 (TRAIN.EVAL_TEXT): logits = p_text                                                   (2851, 2989)
+//   mode 2 (TRAIN.COMBINE)  : logits = p_text^a * softmax_c((8 - cum_dists_visual) / 8)^(1 - a)  (2921-2928), a = TEXT_COFF
+constexpr int TEXT_MAX_WAY = 64;
+__global__ void __launch_bounds__(256)
+text_fusion_kernel(const float* __restrict__ tgt /*[Q,T,E]*/, const float* __restrict__ text_test,
+                   const float* __restrict__ real_labels, const int* __restrict__ cls, const int* __restrict__ counts,
+                   int S, int T, int E, int way, const float* __restrict__ scale, int mode, float text_coff,
+                   const float* __restrict__ cum_visual /*[Q,way] or null*/, float* __restrict__ logits /*[Q,way]*/) {
+    extern __shared__ float sm[];   // img[E]
+    __shared__ float red[8];
+    __shared__ float lg[TEXT_MAX_WAY];
+    const int q = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const float* src = tgt + (size_t)q * T * E;
+    float sq = 0.f;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        float a = 0.f;
+        for (int t = 0; t < T; ++t) a += src[(size_t)t * E + e];
+        a /= float(T);
+        sm[e] = a;
+        sq += a * a;
+    }
+    sq = warp_sum(sq);
+    if (lane == 0) red[warp] = sq;
+    __syncthreads();
+    float xn = 0.f;
+    for (int w = 0; w < nw; ++w) xn += red[w];
+    xn = sqrtf(xn);
+    for (int c = warp; c < way; c += nw) {
+        const float inv = 1.0f / float(counts[c]);
+        float dot = 0.f, tn = 0.f;
+        for (int e = lane; e < E; e += 32) {
+            float tv = 0.f;
+            for (int s = 0; s < S; ++s)
+                if (cls[s] == c) tv += text_test[(size_t)((long long)real_labels[s]) * E + e];
+            tv *= inv;
+            dot = fmaf(sm[e], tv, dot);
+            tn = fmaf(tv, tv, tn);
+        }
+        dot = warp_sum(dot);
+        tn = sqrtf(warp_sum(tn));
+        if (lane == 0) lg[c] = scale[0] * (dot / xn / tn);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mx = -INFINITY;
+        for (int c = 0; c < way; ++c) mx = fmaxf(mx, lg[c]);
+        float sum = 0.f;
+        for (int c = 0; c < way; ++c) { lg[c] = expf(lg[c] - mx); sum += lg[c]; }
+        float vmx = -INFINITY, vsum = 0.f;
+        if (mode == 2) {
+            for (int c = 0; c < way; ++c) vmx = fmaxf(vmx, (8.0f - cum_visual[(size_t)q * way + c]) / 8.0f);
+            for (int c = 0; c < way; ++c) vsum += expf((8.0f - cum_visual[(size_t)q * way + c]) / 8.0f - vmx);
+        }
+        for (int c = 0; c < way; ++c) {
+            const float pt = lg[c] / sum;
+            float out = pt;
+            if (mode == 2) {
+                const float pv = expf((8.0f - cum_visual[(size_t)q * way + c]) / 8.0f - vmx) / vsum;
+                out = powf(pt, text_coff) * powf(pv, 1.0f - text_coff);
+            }
+            logits[(size_t)q * way + c] = out;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Cosine distances + OTAM.  One CTA per (query, class):
 //   dists[i][j] = 1 - q_i . p_j / (|q_i| |p_j| + 0.01)                      (cos_sim 1115-1124, 2973-2976)
 //   cum = OTAM(dists) (+ OTAM(dists^T) unless single_direct)                 (2657-2687, 2979-2982)

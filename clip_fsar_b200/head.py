@@ -6,9 +6,9 @@ reference head CNN_OTAM_CLIPFSAR (models/base/few_shot.py:2690-2993), so `utils/
 of libfsar_sm100.so (clip_fsar_b200/lib.py); PyTorch only owns the fp32 master parameters, device buffers and the
 stream. There is no torch / CPU fallback: forward on a machine without an sm_100 GPU raises.
 
-Scope: the eval else-branch (few_shot.py:2932-2990) honouring TRAIN.MERGE_BEFORE,
-TRAIN.SINGLE_DIRECT, TRAIN.TRANSFORMER_DEPTH and DATA.NUM_INPUT_FRAMES. Training mode and the EVAL_TEXT / COMBINE
-branches (8f-4, "next") raise NotImplementedError.
+Scope: the eval forward (few_shot.py:2834-2990) — the visual else-branch honouring
+TRAIN.MERGE_BEFORE, TRAIN.SINGLE_DIRECT, TRAIN.TRANSFORMER_DEPTH and DATA.NUM_INPUT_FRAMES, and the text branches
+TRAIN.EVAL_TEXT / TRAIN.COMBINE (+ TEXT_COFF). Training mode raises NotImplementedError.
 """
 import os
 import warnings
@@ -115,9 +115,9 @@ class CNN_OTAM_CLIPFSAR_SM100(nn.Module):
         self.num_frames = int(cfg.DATA.NUM_INPUT_FRAMES)
         self.merge_before = bool(_cfg_get(cfg.TRAIN, "MERGE_BEFORE", False))          # 2949
         self.single_direct = bool(_cfg_get(cfg.TRAIN, "SINGLE_DIRECT", False))        # 2979
-        for flag in ("EVAL_TEXT", "COMBINE"):                                         # 2835 / 2855
-            if _cfg_get(cfg.TRAIN, flag, False):
-                raise NotImplementedError("TRAIN.%s eval branch is not part of the sm_100a path yet" % flag)
+        # text branches of the eval forward: EVAL_TEXT wins over COMBINE (few_shot.py:2835 / 2855, if / elif)
+        self.text_mode = 1 if _cfg_get(cfg.TRAIN, "EVAL_TEXT", False) else (2 if _cfg_get(cfg.TRAIN, "COMBINE", False) else 0)
+        self.text_coff = float(_cfg_get(cfg.TRAIN, "TEXT_COFF", 0) or 0.9)            # 2925-2928
         self.class_real_train = list(_cfg_get(cfg.TRAIN, "CLASS_NAME", []) or [])
         self.class_real_test = list(_cfg_get(cfg.TEST, "CLASS_NAME", []) or [])
 
@@ -245,7 +245,8 @@ class CNN_OTAM_CLIPFSAR_SM100(nn.Module):
 
         logits, class_logits = eng.episode_forward(
             f32(support), f32(target), f32(support_labels).reshape(-1), f32(real).reshape(-1), T, way,
-            self.merge_before, self.single_direct, n_train_classes=self.text_features_train.shape[0])
+            self.merge_before, self.single_direct, n_train_classes=self.text_features_train.shape[0],
+            text_mode=self.text_mode, text_coff=self.text_coff)
         return {"logits": logits, "class_logits": class_logits}
 
     def loss(self, task_dict, model_dict):

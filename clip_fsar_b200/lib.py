@@ -22,7 +22,7 @@ SYMBOLS = [
     "fsar_missing_weights", "fsar_missing_weight", "fsar_vit_forward", "fsar_modulate", "fsar_otam_logits",
     "fsar_episode_forward", "fsar_episode_forward_host", "fsar_episode_submit_host", "fsar_episode_collect_host",
     "fsar_episodes_forward", "fsar_episodes_submit_host", "fsar_episodes_collect_host",
-    "fsar_peek", "fsar_operand_dtype", "fsar_op_layernorm", "fsar_op_gemm", "fsar_op_attention", "fsar_op_f32_to_16",
+    "fsar_metrics_update", "fsar_peek", "fsar_operand_dtype", "fsar_op_layernorm", "fsar_op_gemm", "fsar_op_attention", "fsar_op_f32_to_16",
     "fsar_launch_count", "fsar_profile_begin", "fsar_profile_end",
 ]
 
@@ -47,7 +47,8 @@ class FsarEpisode(Structure):
     _fields_ = [
         ("support_frames", c_void_p), ("target_frames", c_void_p), ("support_labels", c_void_p),
         ("real_support_labels", c_void_p), ("n_support", c_int32), ("n_target", c_int32), ("n_frames", c_int32),
-        ("way", c_int32), ("merge_before", c_int32), ("single_direct", c_int32),
+        ("way", c_int32), ("merge_before", c_int32), ("single_direct", c_int32), ("text_mode", c_int32),
+        ("text_coff", c_float),
     ]
 
 
@@ -96,6 +97,7 @@ def load_library(path=None):
     lib.fsar_episodes_forward.argtypes = [H, POINTER(FsarEpisode), c_int, c_void_p, c_void_p, c_void_p]
     lib.fsar_episodes_submit_host.argtypes = [H, c_int, POINTER(FsarEpisode), c_int]
     lib.fsar_episodes_collect_host.argtypes = [H, c_int, c_void_p, c_void_p]
+    lib.fsar_metrics_update.argtypes = [H, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
     lib.fsar_peek.argtypes = [H, c_char_p, c_void_p, c_int64, c_void_p]
     lib.fsar_peek.restype = c_int64
     lib.fsar_operand_dtype.restype = c_int
@@ -233,7 +235,7 @@ class Engine:
         return (logits, dists, cum) if return_intermediates else logits
 
     def _episode(self, support, target, support_labels, real_support_labels, n_frames, way, merge_before,
-                 single_direct):
+                 single_direct, text_mode=0, text_coff=0.9):
         S = support.shape[0] // n_frames
         Q = target.shape[0] // n_frames
         if S * n_frames != support.shape[0] or Q * n_frames != target.shape[0]:
@@ -244,18 +246,22 @@ class Engine:
                              (S, support_labels.numel(), real_support_labels.numel()))
         ep = FsarEpisode(support.data_ptr(), target.data_ptr(), support_labels.data_ptr(),
                          real_support_labels.data_ptr(), S, Q, n_frames, way, int(bool(merge_before)),
-                         int(bool(single_direct)))
+                         int(bool(single_direct)), int(text_mode), float(text_coff))
         return ep, S, Q
 
     def episode_forward(self, support, target, support_labels, real_support_labels, n_frames, way,
-                        merge_before=False, single_direct=False, n_train_classes=None, want_class_logits=True):
-        """Device-resident episode: returns (logits [Q, way], class_logits [S + Q, n_train] or None)."""
+                        merge_before=False, single_direct=False, n_train_classes=None, want_class_logits=True,
+                        text_mode=0, text_coff=0.9):
+        """Device-resident episode: returns (logits [Q, way], class_logits [S + Q, n_train] or None).
+        text_mode 1 / 2 = TRAIN.EVAL_TEXT / TRAIN.COMBINE (class_logits is None there, as in the reference)."""
+        if text_mode:
+            want_class_logits = False
         torch = self._torch
         for name, t in (("support_set", support), ("target_set", target), ("support_labels", support_labels),
                         ("real_support_labels", real_support_labels)):
             self._f32(t, name)
         ep, S, Q = self._episode(support, target, support_labels, real_support_labels, n_frames, way, merge_before,
-                                 single_direct)
+                                 single_direct, text_mode, text_coff)
         logits = torch.empty((Q, way), dtype=torch.float32, device=self.device)
         cl = None
         if want_class_logits:
@@ -330,6 +336,18 @@ class Engine:
         cl = torch.empty((S + Q, int(n_train_classes)), dtype=torch.float32) if n_train_classes else None
         self.episode_collect_host(0, logits, cl)
         return logits, cl
+
+    def metrics_update(self, logits, target_labels, counters, per_class=None):
+        """counters (int64[3], device) += {top-1 hits, queries, round(sum cross-entropy * 1e6)}; no host sync."""
+        torch = self._torch
+        Q, way = logits.reshape(-1, logits.shape[-1]).shape
+        if counters.dtype != torch.int64 or not counters.is_cuda or counters.numel() < 3:
+            raise ValueError("counters must be a CUDA int64 tensor with 3 elements")
+        self._check(self.lib.fsar_metrics_update(
+            self._h, self._f32(logits, "logits"), self._f32(target_labels, "target_labels"), Q, way,
+            c_void_p(counters.data_ptr()), c_void_p(per_class.data_ptr()) if per_class is not None else None,
+            self._stream()))
+        return counters
 
     def peek(self, name, shape, dtype=None):
         torch = self._torch

@@ -34,6 +34,11 @@ def update_counters(counters, logits, target_labels):
     return counters
 
 
+def update_counters_device(engine, counters, logits, target_labels, per_class=None):
+    """Same accumulation as update_counters, as ONE device kernel through the C ABI (fsar_metrics_update)."""
+    return engine.metrics_update(logits, target_labels, counters, per_class)
+
+
 def reduce_counters(counters):
     """The only collective of the path: one SUM all-reduce (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -49,12 +54,17 @@ def summarise(counters):
 
 
 def evaluate(forward_fn, n_episodes, way=5, shot=1, queries_per_class=1, n_frames=8, image_size=224,
-             n_test_classes=24, seed=1000, rank=0, world=1, device="cpu", structured=True):
+             n_test_classes=24, seed=1000, rank=0, world=1, device="cpu", structured=True, engine=None):
     """Run this rank's shard of `n_episodes` seeded synthetic episodes through `forward_fn(task) -> logits` and
-    return the globally reduced summary (identical on every rank)."""
+    return the globally reduced summary (identical on every rank). With `engine` the counters are updated by the
+    library's device kernel, otherwise by the equivalent torch ops (CPU tests)."""
     counters = new_counters(device)
     for i in shard(n_episodes, rank, world):
         ep = synth.synth_episode(way, shot, queries_per_class, n_frames, image_size, n_test_classes, seed + i, structured)
         task = {k: torch.from_numpy(v).to(device, non_blocking=True) for k, v in ep.items()}
-        update_counters(counters, forward_fn(task), task["target_labels"])
+        logits = forward_fn(task)
+        if engine is not None:
+            update_counters_device(engine, counters, logits, task["target_labels"])
+        else:
+            update_counters(counters, logits, task["target_labels"])
     return summarise(reduce_counters(counters))

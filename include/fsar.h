@@ -74,6 +74,10 @@ typedef struct fsar_episode {
     int32_t way;                       /* number of distinct support labels (torch.unique, few_shot.py:2965) */
     int32_t merge_before;              /* TRAIN.MERGE_BEFORE  (few_shot.py:2949) */
     int32_t single_direct;             /* TRAIN.SINGLE_DIRECT (few_shot.py:2979) */
+    int32_t text_mode;                 /* 0 = visual path (default); 1 = TRAIN.EVAL_TEXT (few_shot.py:2835-2852);
+                                          2 = TRAIN.COMBINE (2855-2930). Modes 1/2 return class_logits = None in the
+                                          reference: class_logits_dev is left untouched. */
+    float text_coff;                   /* TRAIN.TEXT_COFF, exponent of the text probability in mode 2 (default 0.9) */
 } fsar_episode;
 
 /* Per-kernel-class device time of the calls issued between fsar_profile_begin/end (CUDA events on `stream`). */
@@ -146,6 +150,12 @@ int fsar_episode_forward_host(fsar_handle* h, const fsar_episode* ep_host, float
  * Lets the copy of episode i+1 overlap the compute of episode i. */
 int fsar_episode_submit_host(fsar_handle* h, int slot, const fsar_episode* ep_host);
 int fsar_episode_collect_host(fsar_handle* h, int slot, float* logits_host, float* class_logits_host);
+
+/* Caller-side metrics (runs/test_net_few_shot.py:111 cross-entropy, 147 topks_correct, 151-160 per-class accuracy) kept
+ * on the device: counters_dev int64[3] += {n_correct_top1, n_queries, round(sum CE * 1e6)}; per_class_dev (may be NULL)
+ * int64[2 * way] += {hits per class | queries per class}. No host synchronisation; read the counters once per run. */
+int fsar_metrics_update(fsar_handle* h, const float* logits_dev, const float* target_labels_dev, int Q, int way,
+                        int64_t* counters_dev, int64_t* per_class_dev, void* stream);
 
 /* Intermediates of the last episode (test taps): "support_feats" [S,T,E], "target_feats" [Q,T,E],
  * "mod_out" [rows,E], "protos" [way,T,E], "dists" [Q,way,T,T], "cum_dists" [Q,way], "class_index" (int32 [S]).

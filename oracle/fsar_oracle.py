@@ -194,8 +194,19 @@ def class_index(labels):
     return torch.stack([(uniq == v).nonzero()[0, 0] for v in labels]), uniq.numel()
 
 
+def text_probabilities(sd, text_test, target_feats, real_support_labels, cls, way):
+    """p_text of the EVAL_TEXT / COMBINE branches, few_shot.py:2836-2849 (= 2857-2870): per-class mean of the support
+    videos' text features, unit-normalised (no epsilon here), softmax over classes of scale * cosine."""
+    txt = _t(text_test).float()[_t(real_support_labels).long()]
+    txt = torch.stack([txt[cls == c].mean(0) for c in range(way)])
+    img = _t(target_feats).float().mean(1)
+    img = img / img.norm(dim=1, keepdim=True)
+    txt = txt / txt.norm(dim=1, keepdim=True)
+    return torch.softmax(sd["scale"] * img @ txt.t(), dim=1)
+
+
 def head_forward(sd, g, text_train, text_test, support_feats, target_feats, support_labels, real_support_labels,
-                 merge_before=False, single_direct=False, lbda=0.5):
+                 merge_before=False, single_direct=False, lbda=0.5, text_mode=0, text_coff=0.9):
     """CNN_OTAM_CLIPFSAR.forward eval else-branch after get_feats, few_shot.py:2936-2990.
     support_feats [S,T,E], target_feats [Q,T,E]. Returns dict with logits, class_logits and intermediates."""
     sd = {k: _t(v) for k, v in sd.items()}
@@ -203,6 +214,9 @@ def head_forward(sd, g, text_train, text_test, support_feats, target_feats, supp
     text_train, text_test = _t(text_train).float(), _t(text_test).float()
     T = sup.shape[1]
     cls, way = class_index(support_labels)
+    if text_mode == 1:                                                                   # TRAIN.EVAL_TEXT, 2835-2852
+        p_text = text_probabilities(sd, text_test, tgt, real_support_labels, cls, way)
+        return {"logits": p_text, "class_logits": None, "class_index": cls}
     # 2936-2939 (classification_layer is an empty nn.Sequential)
     class_logits = cos_sim(torch.cat([sup, tgt], 0).mean(1), text_train) * sd["scale"]
     context = text_test[_t(real_support_labels).long()].unsqueeze(1)                     # 2946
@@ -221,19 +235,25 @@ def head_forward(sd, g, text_train, text_test, support_feats, target_feats, supp
         cum = otam_cum_dist(dists, lbda)
     else:
         cum = otam_cum_dist(dists, lbda) + otam_cum_dist(dists.transpose(2, 3), lbda)
+    if text_mode == 2:                                                                   # TRAIN.COMBINE, 2921-2930
+        p_text = text_probabilities(sd, text_test, tgt, real_support_labels, cls, way)
+        p_vis = torch.softmax((8 - cum) / 8.0, dim=1)
+        return {"logits": p_text.pow(text_coff) * p_vis.pow(1.0 - text_coff), "class_logits": None, "target_mod": tgt_mod,
+                "protos": sup_mod, "dists": dists.contiguous(), "cum_dists": cum, "class_index": cls}
     # 2986-2989: prototypes are already one per sorted class, so the class reduction is the identity
     return {"logits": -cum, "class_logits": class_logits, "target_mod": tgt_mod, "protos": sup_mod,
             "dists": dists.contiguous(), "cum_dists": cum, "class_index": cls}
 
 
 def episode_forward(sd, g, text_train, text_test, task, n_frames, merge_before=False, single_direct=False,
-                    lbda=0.5, operand_dtype=None):
+                    lbda=0.5, operand_dtype=None, text_mode=0, text_coff=0.9):
     """CNN_OTAM_CLIPFSAR.forward (eval), few_shot.py:2772-2990, on a task dict of numpy arrays / tensors."""
     sup = vit_forward(sd, g, task["support_set"], operand_dtype=operand_dtype)            # get_feats 2760-2765
     tgt = vit_forward(sd, g, task["target_set"], operand_dtype=operand_dtype)
     E = sup.shape[-1]
     out = head_forward(sd, g, text_train, text_test, sup.reshape(-1, n_frames, E), tgt.reshape(-1, n_frames, E),
-                       task["support_labels"], task["real_support_labels"], merge_before, single_direct, lbda)
+                       task["support_labels"], task["real_support_labels"], merge_before, single_direct, lbda,
+                       text_mode, text_coff)
     out["support_feats"] = sup.reshape(-1, n_frames, E)
     out["target_feats"] = tgt.reshape(-1, n_frames, E)
     return out

@@ -38,6 +38,10 @@ CASES = {
     "tiny_5w1s_default_init": dict(geom="tiny", way=5, shot=1, T=8, spread=False, structured=False),
     "small_5w1s": dict(geom="small", way=5, shot=1, T=8),
     "vitb16_5w1s": dict(geom="ViT-B/16", way=5, shot=1, T=8),
+    # text branches of the eval forward (few_shot.py:2835-2930)
+    "tiny_5w5s_evaltext": dict(geom="tiny", way=5, shot=5, T=8, eval_text=True),
+    "tiny_5w1s_combine": dict(geom="tiny", way=5, shot=1, T=8, combine=True),
+    "tiny_5w5s_combine_coff05_merge": dict(geom="tiny", way=5, shot=5, T=8, combine=True, text_coff=0.5, merge_before=True),
     # the configuration BASELINE.json names: ViT-B/16 "random-init" (default-style init, unstructured N(0,1) frames)
     "vitb16_5w1s_default_init": dict(geom="ViT-B/16", way=5, shot=1, T=8, spread=False, structured=False, eseed=1001),
 }
@@ -74,6 +78,12 @@ def build_reference(fs, BaseVideoModel, g, n_train, n_test, T, flags):
         train.SINGLE_DIRECT = True
     if flags.get("mod_depth", 1) > 1:
         train.TRANSFORMER_DEPTH = flags["mod_depth"]
+    if flags.get("eval_text"):
+        train.EVAL_TEXT = True
+    if flags.get("combine"):
+        train.COMBINE = True
+    if flags.get("text_coff"):
+        train.TEXT_COFF = flags["text_coff"]
     cfg = NS(TRAIN=train, TEST=NS(CLASS_NAME=["t%d" % i for i in range(n_test)]), DATA=NS(NUM_INPUT_FRAMES=T),
              VIDEO=NS(HEAD=NS(NAME="CNN_OTAM_CLIPFSAR", BACKBONE_NAME="ViT-B/16"), BACKBONE=NS(META_ARCH="Identity")),
              BN=NS(FREEZE=False))
@@ -126,12 +136,18 @@ def run_case(name, fs, BaseVideoModel, out_dir):
     meta = dict(case=name, geom=case["geom"], way=way, shot=shot, T=T, n_train=n_train, n_test=n_test, wseed=wseed,
                 eseed=eseed, spread=case.get("spread", True), structured=case.get("structured", True),
                 merge_before=bool(case.get("merge_before")), single_direct=bool(case.get("single_direct")),
-                mod_depth=case.get("mod_depth", 1), text_seeds=[7, 8], reference_commit="30cf0a8c",
+                mod_depth=case.get("mod_depth", 1), text_seeds=[7, 8],
+                text_mode=1 if case.get("eval_text") else (2 if case.get("combine") else 0),
+                text_coff=case.get("text_coff", 0.9), reference_commit="30cf0a8c",
                 torch=torch.__version__, state_dict_keys=sorted(head.state_dict().keys()))
+    no_ctx = len(taps["context2"]) == 0       # EVAL_TEXT never runs the modulator / OTAM
     arrays = dict(
-        logits=out["logits"].numpy(), class_logits=out["class_logits"].numpy(),
+        logits=out["logits"].numpy(),
+        class_logits=out["class_logits"].numpy() if out["class_logits"] is not None else np.zeros((0,), np.float32),
         support_feats=taps["backbone"][0].reshape(-1, T, E).numpy(), target_feats=taps["backbone"][1].reshape(-1, T, E).numpy(),
-        target_mod=taps["context2"][0].numpy(), support_mod=taps["context2"][1].numpy(), dists=taps["dists"][0].numpy(),
+        target_mod=np.zeros((0,), np.float32) if no_ctx else taps["context2"][0].numpy(),
+        support_mod=np.zeros((0,), np.float32) if no_ctx else taps["context2"][1].numpy(),
+        dists=np.zeros((0,), np.float32) if no_ctx else taps["dists"][0].numpy(),
         # checksums of the regenerated inputs so a test can tell "generator drifted" from "oracle is wrong"
         weight_checksum=np.array([float(np.sum([np.float64(v).sum() for v in sd.values()]))]),
         input_checksum=np.array([float(np.float64(task["support_set"]).sum() + np.float64(task["target_set"]).sum())]),

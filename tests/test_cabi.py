@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(lib):
 def test_config_struct_layout(lib):
     # 17 x 4-byte fields, in header order
     assert ctypes.sizeof(lib.FsarConfig) == 68
-    assert ctypes.sizeof(lib.FsarEpisode) == 4 * 8 + 6 * 4
+    assert ctypes.sizeof(lib.FsarEpisode) == 4 * 8 + 8 * 4
     assert ctypes.sizeof(lib.FsarProfile) == 12 * 8 * 4
 
 

@@ -51,10 +51,11 @@ def test_load_state_dict_round_trip_marks_engine_dirty():
 
 def test_unsupported_branches_raise():
     from clip_fsar_b200.head import CNN_OTAM_CLIPFSAR_SM100
-    with pytest.raises(NotImplementedError):
-        CNN_OTAM_CLIPFSAR_SM100(make_cfg(backbone="tiny", EVAL_TEXT=True))
-    with pytest.raises(NotImplementedError):
-        CNN_OTAM_CLIPFSAR_SM100(make_cfg(backbone="tiny", COMBINE=True))
+    # the text branches are part of the path: EVAL_TEXT wins over COMBINE like the reference's if / elif
+    assert CNN_OTAM_CLIPFSAR_SM100(make_cfg(backbone="tiny", EVAL_TEXT=True, COMBINE=True)).text_mode == 1
+    h = CNN_OTAM_CLIPFSAR_SM100(make_cfg(backbone="tiny", COMBINE=True, TEXT_COFF=0.5))
+    assert h.text_mode == 2 and h.text_coff == 0.5
+    assert CNN_OTAM_CLIPFSAR_SM100(make_cfg(backbone="tiny", COMBINE=True)).text_coff == 0.9
     with pytest.raises(ValueError):
         CNN_OTAM_CLIPFSAR_SM100(make_cfg(backbone="RN50"))
     cfg = make_cfg(backbone="tiny")
