@@ -58,6 +58,8 @@ struct ProfRec {
 };
 
 struct HostSlot {
+    uint8_t* raw_dev = nullptr;    // uint8 staging of the _u8 entry point (grown on demand)
+    size_t raw_bytes = 0;
     float* frames_dev = nullptr;   // [max_videos * max_tokens, 3, S, S]: support first, then target
     float* labels_dev = nullptr;   // [2 * max_videos]: support_labels | real_support_labels
     float* logits_dev = nullptr;   // [max_videos * max_videos]
@@ -896,6 +898,7 @@ void fsar_destroy(fsar_handle* h) {
     for (int i = 0; i < 2; ++i) {
         HostSlot& s = h->slot[i];
         if (s.frames_dev) cudaFree(s.frames_dev);
+        if (s.raw_dev) cudaFree(s.raw_dev);
         if (s.labels_dev) cudaFree(s.labels_dev);
         if (s.logits_dev) cudaFree(s.logits_dev);
         if (s.clogits_dev) cudaFree(s.clogits_dev);
@@ -1043,6 +1046,72 @@ int fsar_episode_collect_host(fsar_handle* h, int slot, float* logits_host, floa
 int fsar_episode_forward_host(fsar_handle* h, const fsar_episode* ep, float* logits_host, float* class_logits_host) {
     RET_IF(fsar_episodes_submit_host(h, 0, ep, 1));
     return fsar_episodes_collect_host(h, 0, logits_host, class_logits_host);
+}
+
+static int preprocess_u8(fsar_handle* h, const uint8_t* src, int n, int H, int W, int rh, int rw, const float* mean,
+                         const float* std, float* dst, cudaStream_t st) {
+    const int S = h->cfg.image_size;
+    if (n < 1 || H < 1 || W < 1 || rh < S || rw < S || mean == nullptr || std == nullptr)
+        return fail(h, FSAR_E_INVALID, "preprocess: bad geometry (n %d, source %dx%d, resize %dx%d, crop %d)", n, H, W, rh, rw, S);
+    PreprocParams pp;
+    pp.n = n; pp.H = H; pp.W = W; pp.RH = rh; pp.RW = rw; pp.S = S;
+    for (int c = 0; c < 3; ++c) { pp.mean[c] = mean[c]; pp.std[c] = std[c]; }
+    const long long total = (long long)n * S * S;
+    Scope s(h, st, FSAR_K_PATCH_GATHER, 0.0, (double)n * (3.0 * H * W + 12.0 * S * S));
+    preprocess_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, dst, pp);
+    return check_launch(h, "preprocess_u8_kernel");
+}
+
+int fsar_preprocess_u8(fsar_handle* h, const uint8_t* frames_u8_dev, int n_frames, int H, int W, int resize_h, int resize_w,
+                       const float mean[3], const float std[3], float* out_dev, void* stream) {
+    if (h == nullptr || frames_u8_dev == nullptr || out_dev == nullptr) return fail(h, FSAR_E_INVALID, "fsar_preprocess_u8: NULL argument");
+    return preprocess_u8(h, frames_u8_dev, n_frames, H, W, resize_h, resize_w, mean, std, out_dev, (cudaStream_t)stream);
+}
+
+int fsar_episodes_submit_host_u8(fsar_handle* h, int slot, const fsar_episode* eps, int n_episodes, int H, int W,
+                                 int resize_h, int resize_w, const float mean[3], const float std[3]) {
+    if (h == nullptr || slot < 0 || slot > 1) return fail(h, FSAR_E_INVALID, "fsar_episodes_submit_host_u8: bad argument");
+    RET_IF(check_batch(h, eps, n_episodes));
+    CU_OK(h, cudaSetDevice(h->cfg.device));
+    RET_IF(ensure_host_path(h));
+    HostSlot& s = h->slot[slot];
+    if (s.busy) return fail(h, FSAR_E_STATE, "slot %d still holds uncollected episodes", slot);
+    const fsar_config& c = h->cfg;
+    const size_t frame_elems = (size_t)3 * c.image_size * c.image_size, raw_frame = (size_t)H * W * 3;
+    size_t total_frames = 0;
+    for (int i = 0; i < n_episodes; ++i) total_frames += (size_t)(eps[i].n_support + eps[i].n_target) * eps[i].n_frames;
+    if (total_frames * raw_frame > s.raw_bytes) {
+        if (s.raw_dev) { CU_OK(h, cudaStreamSynchronize(h->compute_stream)); cudaFree(s.raw_dev); s.raw_dev = nullptr; }
+        CU_OK(h, cudaMalloc(&s.raw_dev, total_frames * raw_frame));
+        s.raw_bytes = total_frames * raw_frame;
+    }
+    std::vector<fsar_episode> dev(eps, eps + n_episodes);
+    size_t f_off = 0, n_logits = 0, n_clogits = 0;   // f_off in frames
+    for (int i = 0; i < n_episodes; ++i) {
+        const fsar_episode& ep = eps[i];
+        const size_t ns = (size_t)ep.n_support * ep.n_frames, nt = (size_t)ep.n_target * ep.n_frames;
+        float* lab = s.labels_dev + (size_t)i * 2 * c.max_videos;
+        CU_OK(h, cudaMemcpyAsync(s.raw_dev + f_off * raw_frame, ep.support_frames, ns * raw_frame, cudaMemcpyHostToDevice, h->copy_stream));
+        CU_OK(h, cudaMemcpyAsync(s.raw_dev + (f_off + ns) * raw_frame, ep.target_frames, nt * raw_frame, cudaMemcpyHostToDevice, h->copy_stream));
+        CU_OK(h, cudaMemcpyAsync(lab, ep.support_labels, sizeof(float) * ep.n_support, cudaMemcpyHostToDevice, h->copy_stream));
+        CU_OK(h, cudaMemcpyAsync(lab + c.max_videos, ep.real_support_labels, sizeof(float) * ep.n_support, cudaMemcpyHostToDevice, h->copy_stream));
+        dev[i].support_frames = s.frames_dev + f_off * frame_elems;
+        dev[i].target_frames = s.frames_dev + (f_off + ns) * frame_elems;
+        dev[i].support_labels = lab;
+        dev[i].real_support_labels = lab + c.max_videos;
+        f_off += ns + nt;
+        n_logits += (size_t)ep.n_target * ep.way;
+        n_clogits += (size_t)(ep.n_support + ep.n_target) * h->n_text_train;
+    }
+    CU_OK(h, cudaEventRecord(s.copied, h->copy_stream));
+    CU_OK(h, cudaStreamWaitEvent(h->compute_stream, s.copied, 0));
+    RET_IF(preprocess_u8(h, s.raw_dev, (int)total_frames, H, W, resize_h, resize_w, mean, std, s.frames_dev, h->compute_stream));
+    RET_IF(episodes_forward_dev(h, dev.data(), n_episodes, s.logits_dev, s.clogits_dev, h->compute_stream));
+    CU_OK(h, cudaMemcpyAsync(s.logits_pin, s.logits_dev, sizeof(float) * n_logits, cudaMemcpyDeviceToHost, h->compute_stream));
+    CU_OK(h, cudaMemcpyAsync(s.clogits_pin, s.clogits_dev, sizeof(float) * n_clogits, cudaMemcpyDeviceToHost, h->compute_stream));
+    CU_OK(h, cudaEventRecord(s.done, h->compute_stream));
+    s.n_logits = n_logits; s.n_clogits = n_clogits; s.busy = 1;
+    return 0;
 }
 
 int fsar_metrics_update(fsar_handle* h, const float* logits_dev, const float* target_labels_dev, int Q, int way,

@@ -10,6 +10,49 @@
 namespace fsar {
 
 // ------------------------------------------------------------------------------------------------
+// Test-time frame pre-processing of the reference loader, fused: ToTensorVideo (uint8 THWC -> float / 255),
+// KineticsResizedCropFewshot (bilinear resize to RH x RW with align_corners = False, then the centre S x S crop;
+// datasets/utils/transformations.py:676-716 with idx = TEST_CENTER_CROP, one spatial crop) and NormalizeVideo
+// ((x - mean) / std; datasets/base/ssv2_few_shot.py:633-642). uint8 [n, H, W, 3] -> fp32 [n, 3, S, S], i.e. exactly
+// the `support_set` / `target_set` tensors of the task dict, so raw frames can cross PCIe as bytes (4x fewer than fp32
+// crops, more for larger source frames). One thread per output pixel, the three channels together.
+struct PreprocParams {
+    int n, H, W, RH, RW, S;
+    float mean[3], std[3];
+};
+__global__ void __launch_bounds__(256)
+preprocess_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, const PreprocParams p) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)p.n * p.S * p.S;
+    if (idx >= total) return;
+    const int x = int(idx % p.S);
+    const int y = int((idx / p.S) % p.S);
+    const int f = int(idx / ((long long)p.S * p.S));
+    const int ry = y + (p.RH - p.S) / 2, rx = x + (p.RW - p.S) / 2;      // position in the resized frame
+    // torch upsample_bilinear2d, align_corners = False: src = scale * (dst + 0.5) - 0.5, clamped at 0
+    const float sh = float(p.H) / float(p.RH), sw = float(p.W) / float(p.RW);
+    float fy = sh * (float(ry) + 0.5f) - 0.5f, fx = sw * (float(rx) + 0.5f) - 0.5f;
+    fy = fy < 0.f ? 0.f : fy;
+    fx = fx < 0.f ? 0.f : fx;
+    const int y0 = int(fy), x0 = int(fx);
+    const int y1 = y0 + (y0 < p.H - 1 ? 1 : 0), x1 = x0 + (x0 < p.W - 1 ? 1 : 0);
+    const float ly1 = fy - float(y0), lx1 = fx - float(x0);
+    const float ly0 = 1.0f - ly1, lx0 = 1.0f - lx1;
+    const uint8_t* base = src + (size_t)f * p.H * p.W * 3;
+    const uint8_t* p00 = base + ((size_t)y0 * p.W + x0) * 3;
+    const uint8_t* p01 = base + ((size_t)y0 * p.W + x1) * 3;
+    const uint8_t* p10 = base + ((size_t)y1 * p.W + x0) * 3;
+    const uint8_t* p11 = base + ((size_t)y1 * p.W + x1) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float v00 = float(p00[c]) / 255.0f, v01 = float(p01[c]) / 255.0f;
+        const float v10 = float(p10[c]) / 255.0f, v11 = float(p11[c]) / 255.0f;
+        const float v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+        dst[(((size_t)f * 3 + c) * p.S + y) * p.S + x] = (v - p.mean[c]) / p.std[c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Patch gather: frames NCHW fp32 [n, 3, S, S] -> A16 [n * G * G, Kp], k = c * P * P + ky * P + kx
 // (the flattening of conv1.weight [width, 3, P, P], few_shot.py:659,672). One thread per (frame, c, y, px):
 // it reads P contiguous floats and writes P contiguous 16-bit values. Columns [3 P P, Kp) are never

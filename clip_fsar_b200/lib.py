@@ -22,7 +22,7 @@ SYMBOLS = [
     "fsar_missing_weights", "fsar_missing_weight", "fsar_vit_forward", "fsar_modulate", "fsar_otam_logits",
     "fsar_episode_forward", "fsar_episode_forward_host", "fsar_episode_submit_host", "fsar_episode_collect_host",
     "fsar_episodes_forward", "fsar_episodes_submit_host", "fsar_episodes_collect_host",
-    "fsar_metrics_update", "fsar_peek", "fsar_operand_dtype", "fsar_op_layernorm", "fsar_op_gemm", "fsar_op_attention", "fsar_op_f32_to_16",
+    "fsar_preprocess_u8", "fsar_episodes_submit_host_u8", "fsar_metrics_update", "fsar_peek", "fsar_operand_dtype", "fsar_op_layernorm", "fsar_op_gemm", "fsar_op_attention", "fsar_op_f32_to_16",
     "fsar_launch_count", "fsar_profile_begin", "fsar_profile_end",
 ]
 
@@ -97,6 +97,9 @@ def load_library(path=None):
     lib.fsar_episodes_forward.argtypes = [H, POINTER(FsarEpisode), c_int, c_void_p, c_void_p, c_void_p]
     lib.fsar_episodes_submit_host.argtypes = [H, c_int, POINTER(FsarEpisode), c_int]
     lib.fsar_episodes_collect_host.argtypes = [H, c_int, c_void_p, c_void_p]
+    F3 = c_float * 3
+    lib.fsar_preprocess_u8.argtypes = [H, c_void_p, c_int, c_int, c_int, c_int, c_int, F3, F3, c_void_p, c_void_p]
+    lib.fsar_episodes_submit_host_u8.argtypes = [H, c_int, POINTER(FsarEpisode), c_int, c_int, c_int, c_int, c_int, F3, F3]
     lib.fsar_metrics_update.argtypes = [H, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
     lib.fsar_peek.argtypes = [H, c_char_p, c_void_p, c_int64, c_void_p]
     lib.fsar_peek.restype = c_int64
@@ -336,6 +339,45 @@ class Engine:
         cl = torch.empty((S + Q, int(n_train_classes)), dtype=torch.float32) if n_train_classes else None
         self.episode_collect_host(0, logits, cl)
         return logits, cl
+
+    # CLIP normalisation constants of the shipped configs (DATA.MEAN / DATA.STD, CLIPFSAR_K100_1shot_v1.yaml)
+    CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+    CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+    def preprocess_u8(self, frames_u8, resize=(256, 256), mean=None, std=None):
+        """uint8 [n, H, W, 3] CUDA -> fp32 [n, 3, S, S]: the reference loader's test-time transform, on the device."""
+        torch = self._torch
+        if not (frames_u8.is_cuda and frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous() and frames_u8.dim() == 4
+                and frames_u8.shape[3] == 3):
+            raise ValueError("frames_u8 must be a contiguous uint8 CUDA tensor [n, H, W, 3]")
+        n, Hh, Ww, _ = frames_u8.shape
+        S = self.cfg.image_size
+        out = torch.empty((n, 3, S, S), dtype=torch.float32, device=self.device)
+        F3 = c_float * 3
+        self._check(self.lib.fsar_preprocess_u8(self._h, c_void_p(frames_u8.data_ptr()), n, Hh, Ww, int(resize[0]),
+                                                int(resize[1]), F3(*(mean or self.CLIP_MEAN)), F3(*(std or self.CLIP_STD)),
+                                                c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def episodes_submit_host_u8(self, slot, episodes, n_frames, way, resize=(256, 256), mean=None, std=None,
+                                merge_before=False, single_direct=False):
+        """`episodes`: list of (support_u8 [S*T, H, W, 3], target_u8 [Q*T, H, W, 3], support_labels, real_support_labels)
+        HOST tensors (uint8 frames, fp32 labels). Raw bytes cross PCIe; pre-processing runs on the device."""
+        torch = self._torch
+        n = len(episodes)
+        arr = (FsarEpisode * n)()
+        Hh, Ww = episodes[0][0].shape[1:3]
+        for i, (sup, tgt, sl, rl) in enumerate(episodes):
+            for name, t in (("support_u8", sup), ("target_u8", tgt)):
+                if t.is_cuda or t.dtype != torch.uint8 or not t.is_contiguous() or tuple(t.shape[1:]) != (Hh, Ww, 3):
+                    raise ValueError("%s must be a contiguous uint8 HOST tensor [frames, %d, %d, 3]" % (name, Hh, Ww))
+            S, Q = sup.shape[0] // n_frames, tgt.shape[0] // n_frames
+            arr[i] = FsarEpisode(sup.data_ptr(), tgt.data_ptr(), sl.data_ptr(), rl.data_ptr(), S, Q, n_frames, way,
+                                 int(bool(merge_before)), int(bool(single_direct)), 0, 0.9)
+        F3 = c_float * 3
+        self._check(self.lib.fsar_episodes_submit_host_u8(self._h, slot, arr, n, Hh, Ww, int(resize[0]), int(resize[1]),
+                                                          F3(*(mean or self.CLIP_MEAN)), F3(*(std or self.CLIP_STD))))
+        return n, S, Q
 
     def metrics_update(self, logits, target_labels, counters, per_class=None):
         """counters (int64[3], device) += {top-1 hits, queries, round(sum cross-entropy * 1e6)}; no host sync."""

@@ -145,6 +145,15 @@ def synth_episode(way=5, shot=1, queries_per_class=1, n_frames=8, image_size=224
     }
 
 
+def synth_raw_frames(n_frames, height, width, seed=77):
+    """uint8 [n, H, W, 3] "camera" frames (8x8 blocks plus noise, so interpolation errors are visible) for the
+    pre-processing path; regenerated from the seed by tests instead of being stored in the fixtures."""
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, size=(n_frames, height // 8 + 1, width // 8 + 1, 3))
+    frames = np.kron(base, np.ones((1, 8, 8, 1), dtype=np.int64))[:, :height, :width, :]
+    return np.clip(frames + rng.integers(-20, 21, size=frames.shape), 0, 255).astype(np.uint8)
+
+
 # Algorithmic FLOPs of the frame encoder (SURVEY.md 8d): 2 * MAC of patch-embed, QKV, QK^T, PV, out-proj, fc1, fc2
 # and the final projection; no padding, no element-wise work.
 def vit_flops_per_frame(g):

@@ -151,6 +151,18 @@ int fsar_episode_forward_host(fsar_handle* h, const fsar_episode* ep_host, float
 int fsar_episode_submit_host(fsar_handle* h, int slot, const fsar_episode* ep_host);
 int fsar_episode_collect_host(fsar_handle* h, int slot, float* logits_host, float* class_logits_host);
 
+/* Frame pre-processing of the reference's test-time loader, fused on the device:
+ * ToTensorVideo -> KineticsResizedCropFewshot(bilinear resize to resize_h x resize_w, centre crop image_size) ->
+ * NormalizeVideo (datasets/base/ssv2_few_shot.py:633-642, datasets/utils/transformations.py:676-716).
+ * frames_u8_dev uint8 [n_frames, H, W, 3] -> out_dev fp32 [n_frames, 3, image_size, image_size] (task-dict layout). */
+int fsar_preprocess_u8(fsar_handle* h, const uint8_t* frames_u8_dev, int n_frames, int H, int W, int resize_h, int resize_w,
+                       const float mean[3], const float std[3], float* out_dev, void* stream);
+/* fsar_episodes_submit_host with RAW uint8 frames: support_frames / target_frames of each episode point to HOST uint8
+ * [videos * n_frames, H, W, 3]; the bytes are copied as they are and pre-processed on the device (4x less H2D traffic
+ * than fp32 crops at 224 x 224 sources). Collect with fsar_episodes_collect_host. */
+int fsar_episodes_submit_host_u8(fsar_handle* h, int slot, const fsar_episode* eps_host_u8, int n_episodes, int H, int W,
+                                 int resize_h, int resize_w, const float mean[3], const float std[3]);
+
 /* Caller-side metrics (runs/test_net_few_shot.py:111 cross-entropy, 147 topks_correct, 151-160 per-class accuracy) kept
  * on the device: counters_dev int64[3] += {n_correct_top1, n_queries, round(sum CE * 1e6)}; per_class_dev (may be NULL)
  * int64[2 * way] += {hits per class | queries per class}. No host synchronisation; read the counters once per run. */

@@ -186,6 +186,21 @@ def otam_scalar(d, lbda=0.5):
     return c[L - 1][M + 1]
 
 
+def preprocess_u8(frames_u8, crop, resize=(256, 256), mean=(0.48145466, 0.4578275, 0.40821073),
+                  std=(0.26862954, 0.26130258, 0.27577711)):
+    """Test-time loader transform of the reference, restated: ToTensorVideo (uint8 [T,H,W,C] -> float / 255),
+    KineticsResizedCropFewshot._get_controlled_crop with short_side_range = [TEST_SCALE, TEST_SCALE], one spatial crop,
+    idx = TEST_CENTER_CROP (bilinear resize, align_corners = False, then the centre crop; transformations.py:676-716)
+    and NormalizeVideo (ssv2_few_shot.py:633-642). Returns fp32 [T, 3, crop, crop] (the task-dict frame layout)."""
+    x = _t(frames_u8).float().permute(0, 3, 1, 2) / 255.0                              # [T, C, H, W]
+    x = torch.nn.functional.interpolate(x, size=(int(resize[0]), int(resize[1])), mode="bilinear", align_corners=False)
+    y0, x0 = (int(resize[0]) - crop) // 2, (int(resize[1]) - crop) // 2
+    x = x[:, :, y0:y0 + crop, x0:x0 + crop]
+    m = torch.tensor(mean, dtype=torch.float32).view(1, 3, 1, 1)
+    sd = torch.tensor(std, dtype=torch.float32).view(1, 3, 1, 1)
+    return ((x - m) / sd).contiguous()
+
+
 def class_index(labels):
     """Rank of each label among the sorted distinct labels: torch.unique(support_labels) is sorted
     (few_shot.py:2950/2960/2965) and extract_class_indices (1127-1136) selects by equality."""

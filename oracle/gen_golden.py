@@ -159,6 +159,36 @@ def run_case(name, fs, BaseVideoModel, out_dir):
         name, lg.mean(), (lg.max(1) - lg.min(1)).mean(), lg.argmax(1).tolist(), path, os.path.getsize(path) // 1024))
 
 
+PREPROC_CASES = {
+    # name: source H, W, frames, TEST_SCALE (resize), TEST_CROP_SIZE, stored pixel stride
+    "preproc_240x320_to_224": dict(H=240, W=320, T=2, scale=256, crop=224, stride=5),
+    "preproc_360x640_to_224": dict(H=360, W=640, T=1, scale=256, crop=224, stride=5),
+    "preproc_128x171_to_224": dict(H=128, W=171, T=2, scale=256, crop=224, stride=5),      # up-sampling
+    "preproc_48x64_to_32": dict(H=48, W=64, T=4, scale=40, crop=32, stride=1),             # the tiny tower's frame size
+}
+
+
+def run_preproc_case(name, out_dir):
+    """Frames through the reference's OWN transform objects, composed exactly as datasets/base/ssv2_few_shot.py:615-642
+    composes them at test time."""
+    import torchvision.transforms._transforms_video as transforms
+    from torchvision.transforms import Compose
+    from datasets.utils.transformations import KineticsResizedCropFewshot
+    c = PREPROC_CASES[name]
+    mean, std = [0.48145466, 0.4578275, 0.40821073], [0.26862954, 0.26130258, 0.27577711]
+    resize = KineticsResizedCropFewshot(short_side_range=[c["scale"], c["scale"]], crop_size=c["crop"], num_spatial_crops=1, idx=1)
+    tf = Compose([transforms.ToTensorVideo(), resize, transforms.NormalizeVideo(mean=mean, std=std, inplace=True)])
+    frames = synth.synth_raw_frames(c["T"], c["H"], c["W"], seed=77)
+    out = tf(torch.from_numpy(frames)).permute(1, 0, 2, 3).contiguous().numpy()          # [C,T,H,W] -> [T,C,H,W] (get_seq)
+    st = c["stride"]
+    meta = dict(case=name, seed=77, **c, mean=mean, std=std, reference_commit="30cf0a8c")
+    path = os.path.join(out_dir, name + ".npz")
+    np.savez_compressed(path, meta=np.array(json.dumps(meta)), out_sub=out[:, :, ::st, ::st],
+                        frames_checksum=np.array([np.int64(frames.astype(np.int64).sum())]),
+                        out_checksum=np.array([np.float64(out).sum(), np.float64(np.abs(out)).sum()]))
+    print("%-28s out %s -> %s (%d KB)" % (name, out.shape, path, os.path.getsize(path) // 1024))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -172,6 +202,10 @@ def main():
         if a.only and name != a.only:
             continue
         run_case(name, fs, BaseVideoModel, a.out)
+    for name in PREPROC_CASES:
+        if a.only and name != a.only:
+            continue
+        run_preproc_case(name, a.out)
 
 
 if __name__ == "__main__":

@@ -17,7 +17,8 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+    """Episode fixtures (the preproc_* fixtures belong to tests/test_preprocess.py)."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("preproc_"))
 
 
 def load_golden(name):
