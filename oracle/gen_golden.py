@@ -38,6 +38,8 @@ CASES = {
     "tiny_5w1s_default_init": dict(geom="tiny", way=5, shot=1, T=8, spread=False, structured=False),
     "small_5w1s": dict(geom="small", way=5, shot=1, T=8),
     "vitb16_5w1s": dict(geom="ViT-B/16", way=5, shot=1, T=8),
+    # largest corner of BASELINE.json's sweep: 20-way 5-shot, 32 frames (100 support + 20 query videos, 3840 frames)
+    "tiny_20w5s_T32_merge": dict(geom="tiny", way=20, shot=5, T=32, merge_before=True, slim=True),
     # text branches of the eval forward (few_shot.py:2835-2930)
     "tiny_5w5s_evaltext": dict(geom="tiny", way=5, shot=5, T=8, eval_text=True),
     "tiny_5w1s_combine": dict(geom="tiny", way=5, shot=1, T=8, combine=True),
@@ -152,6 +154,9 @@ def run_case(name, fs, BaseVideoModel, out_dir):
         weight_checksum=np.array([float(np.sum([np.float64(v).sum() for v in sd.values()]))]),
         input_checksum=np.array([float(np.float64(task["support_set"]).sum() + np.float64(task["target_set"]).sum())]),
     )
+    if case.get("slim"):     # big episodes: keep the outputs, drop the MB-sized intermediates
+        for k in ("support_feats", "target_feats", "target_mod", "support_mod", "dists"):
+            arrays[k] = np.zeros((0,), np.float32)
     path = os.path.join(out_dir, name + ".npz")
     np.savez_compressed(path, meta=np.array(json.dumps(meta)), **arrays)
     lg = arrays["logits"]

@@ -61,9 +61,11 @@ def test_episode_matches_reference_fixture(lib, name):
     S, Q, T, E, way = meta["way"] * meta["shot"], meta["way"], meta["T"], g["embed_dim"], meta["way"]
     tol_logits = 3e-3 if meta["spread"] else 1e-3
     mode = meta.get("text_mode", 0)
-    assert rel_l2(e.peek("support_feats", (S, T, E)), ref["support_feats"]) < 5e-3
-    assert rel_l2(e.peek("target_feats", (Q, T, E)), ref["target_feats"]) < 5e-3
-    if mode != 1:
+    slim = ref["support_feats"].size == 0
+    if not slim:
+        assert rel_l2(e.peek("support_feats", (S, T, E)), ref["support_feats"]) < 5e-3
+        assert rel_l2(e.peek("target_feats", (Q, T, E)), ref["target_feats"]) < 5e-3
+    if mode != 1 and not slim:
         assert float(np.abs(e.peek("dists", (Q, way, T, T)).numpy() - ref["dists"]).max()) < 3e-3
     assert rel_max(logits, ref["logits"]) < tol_logits
     assert logits.shape == ref["logits"].shape

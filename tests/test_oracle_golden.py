@@ -25,9 +25,11 @@ def test_oracle_matches_reference_outputs(name):
     out = O.episode_forward(sd, g, tt, te, task, meta["T"], meta["merge_before"], meta["single_direct"],
                             text_mode=meta.get("text_mode", 0), text_coff=meta.get("text_coff", 0.9))
     # fp32 vs fp32: only summation-order noise is allowed
-    assert rel(out["support_feats"], ref["support_feats"]) < 2e-5
-    assert rel(out["target_feats"], ref["target_feats"]) < 2e-5
-    if meta.get("text_mode", 0) != 1:          # EVAL_TEXT never runs the modulator / OTAM
+    slim = ref["support_feats"].size == 0      # big episodes keep only the outputs in the fixture
+    if not slim:
+        assert rel(out["support_feats"], ref["support_feats"]) < 2e-5
+        assert rel(out["target_feats"], ref["target_feats"]) < 2e-5
+    if meta.get("text_mode", 0) != 1 and not slim:          # EVAL_TEXT never runs the modulator / OTAM
         assert rel(out["target_mod"], ref["target_mod"]) < 2e-5
         assert rel(out["dists"], ref["dists"]) < 1e-5
     assert rel(out["logits"], ref["logits"]) < 1e-5
