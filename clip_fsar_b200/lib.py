@@ -11,7 +11,8 @@ import os
 from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
 
 LIB_NAME = "libfsar_sm100.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+# FSAR_LIB_PATH selects another build of the same sources (e.g. the -DFSAR_BF16 operand-type variant)
+LIB_PATH = os.environ.get("FSAR_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 FSAR_PROF_CLASSES = 12
 EPI_STORE16, EPI_QGELU16, EPI_RESID32, EPI_PATCH32, EPI_STORE32 = 0, 1, 2, 3, 4
