@@ -51,6 +51,15 @@ struct Weight {
     bool required = true;
 };
 
+// Workspace of one episode's head (modulator, prototypes, cos/OTAM). One per episode slot of a batched call, so the
+// heads of the episodes of one fsar_episodes_* call can run concurrently on side streams.
+struct HeadWs {
+    float *seq = nullptr, *mod_ln = nullptr, *mod_qkvbuf = nullptr, *mod_att = nullptr, *mod_y = nullptr, *mod_h = nullptr,
+          *mod_out = nullptr, *mod_tmp = nullptr;
+    float *protos = nullptr, *dists = nullptr, *cum = nullptr;
+    int *cls = nullptr, *counts = nullptr;
+};
+
 struct ProfRec {
     int cls;
     cudaEvent_t a, b;
@@ -88,10 +97,11 @@ struct fsar_handle {
     float* x32 = nullptr;
     // ---- head workspace
     float *feats = nullptr;  // [max_videos * max_tokens, E] support rows then target rows
-    float *seq = nullptr, *mod_ln = nullptr, *mod_qkvbuf = nullptr, *mod_att = nullptr, *mod_y = nullptr,
-          *mod_h = nullptr, *mod_out = nullptr, *mod_tmp = nullptr;
-    float *protos = nullptr, *dists = nullptr, *cum = nullptr;
-    int *cls = nullptr, *counts = nullptr;
+    std::vector<HeadWs> ws;                       // [max_batch]
+    std::vector<cudaStream_t> head_streams;       // [max_batch] side streams for concurrent heads
+    std::vector<cudaEvent_t> head_done;           // [max_batch]
+    cudaEvent_t head_fork = nullptr;
+    int last_ws = 0;
     // last episode geometry (for fsar_peek)
     int last_S = 0, last_Q = 0, last_T = 0, last_way = 0, last_rows = 0;
     const float *last_sup = nullptr, *last_tgt = nullptr;
@@ -479,19 +489,31 @@ int alloc_workspace(fsar_handle* h) {
     const size_t rows = V * (T + 1);
     const size_t inner = (size_t)c.mod_heads * c.mod_dim_head;
     RET_IF(dalloc(h, &h->feats, (size_t)c.max_batch * V * T * E));
-    RET_IF(dalloc(h, &h->seq, rows * E));
-    RET_IF(dalloc(h, &h->mod_ln, rows * E));
-    RET_IF(dalloc(h, &h->mod_qkvbuf, rows * 3 * inner));
-    RET_IF(dalloc(h, &h->mod_att, rows * inner));
-    RET_IF(dalloc(h, &h->mod_y, rows * E));
-    RET_IF(dalloc(h, &h->mod_h, rows * (size_t)c.mod_mlp_dim));
-    RET_IF(dalloc(h, &h->mod_out, rows * E));
-    RET_IF(dalloc(h, &h->mod_tmp, rows * E));
-    RET_IF(dalloc(h, &h->protos, V * T * E));
-    RET_IF(dalloc(h, &h->dists, V * V * T * T));
-    RET_IF(dalloc(h, &h->cum, V * V));
-    RET_IF(dalloc(h, &h->cls, V));
-    RET_IF(dalloc(h, &h->counts, V));
+    h->ws.resize(c.max_batch);
+    for (HeadWs& w : h->ws) {
+        RET_IF(dalloc(h, &w.seq, rows * E));
+        RET_IF(dalloc(h, &w.mod_ln, rows * E));
+        RET_IF(dalloc(h, &w.mod_qkvbuf, rows * 3 * inner));
+        RET_IF(dalloc(h, &w.mod_att, rows * inner));
+        RET_IF(dalloc(h, &w.mod_y, rows * E));
+        RET_IF(dalloc(h, &w.mod_h, rows * (size_t)c.mod_mlp_dim));
+        RET_IF(dalloc(h, &w.mod_out, rows * E));
+        RET_IF(dalloc(h, &w.mod_tmp, rows * E));
+        RET_IF(dalloc(h, &w.protos, V * T * E));
+        RET_IF(dalloc(h, &w.dists, V * V * T * T));
+        RET_IF(dalloc(h, &w.cum, V * V));
+        RET_IF(dalloc(h, &w.cls, V));
+        RET_IF(dalloc(h, &w.counts, V));
+    }
+    if (c.max_batch > 1) {
+        h->head_streams.assign(c.max_batch, nullptr);
+        h->head_done.assign(c.max_batch, nullptr);
+        for (int i = 0; i < c.max_batch; ++i) {
+            CU_OK(h, cudaStreamCreateWithFlags(&h->head_streams[i], cudaStreamNonBlocking));
+            CU_OK(h, cudaEventCreateWithFlags(&h->head_done[i], cudaEventDisableTiming));
+        }
+        CU_OK(h, cudaEventCreateWithFlags(&h->head_fork, cudaEventDisableTiming));
+    }
     return 0;
 }
 
@@ -614,7 +636,7 @@ int vit_encode_segments(fsar_handle* h, const float* const* ptrs, const int* cou
 
 // ---------------------------------------------------------------- temporal prototype modulator
 // x [rows, E]: n_q sequences of T tokens followed by n_s sequences of T + 1 tokens -> out [rows, E]
-int modulate_rows(fsar_handle* h, const float* x, int n_q, int n_s, int T, float* out, cudaStream_t st) {
+int modulate_rows(fsar_handle* h, HeadWs& w, const float* x, int n_q, int n_s, int T, float* out, cudaStream_t st) {
     const fsar_config& c = h->cfg;
     const int E = c.embed_dim, inner = c.mod_heads * c.mod_dim_head, F = c.mod_mlp_dim;
     const int rows = n_q * T + n_s * (T + 1);
@@ -623,24 +645,24 @@ int modulate_rows(fsar_handle* h, const float* x, int n_q, int n_s, int T, float
     for (int l = 0; l < c.mod_depth; ++l) {
         const std::string p = "context2.layers." + std::to_string(l) + ".";
         // depth > 1: intermediate layers ping-pong between mod_tmp and seq (seq is dead once layer 0 consumed it)
-        float* dst = (l == c.mod_depth - 1) ? out : ((l & 1) ? h->seq : h->mod_tmp);
-        RET_IF(layernorm(h, cur, h->mod_ln, W32(h, p + "0.norm.weight"), W32(h, p + "0.norm.bias"), rows, E, false, false,
+        float* dst = (l == c.mod_depth - 1) ? out : ((l & 1) ? w.seq : w.mod_tmp);
+        RET_IF(layernorm(h, cur, w.mod_ln, W32(h, p + "0.norm.weight"), W32(h, p + "0.norm.bias"), rows, E, false, false,
                          1, nullptr, nullptr, st, FSAR_K_MODULATOR));
-        RET_IF(linear_f32<LIN_NONE>(h, h->mod_ln, h->mod_qkv[l], nullptr, nullptr, h->mod_qkvbuf, rows, 3 * inner, E, st));
+        RET_IF(linear_f32<LIN_NONE>(h, w.mod_ln, h->mod_qkv[l], nullptr, nullptr, w.mod_qkvbuf, rows, 3 * inner, E, st));
         {
             const int nmax = T + 1, dh = c.mod_dim_head;
             const size_t smem = sizeof(float) * ((size_t)3 * nmax * dh + (size_t)nmax * (nmax + 1));
             Scope s(h, st, FSAR_K_MODULATOR, 4.0 * rows * nmax * inner, 4.0 * 4.0 * rows * inner);
             modulator_attention_kernel<<<dim3(n_q + n_s, c.mod_heads), 128, smem, st>>>(
-                h->mod_qkvbuf, h->mod_qkvbuf + inner, h->mod_qkvbuf + 2 * inner, h->mod_att, n_q, T, 3 * inner, inner, dh,
+                w.mod_qkvbuf, w.mod_qkvbuf + inner, w.mod_qkvbuf + 2 * inner, w.mod_att, n_q, T, 3 * inner, inner, dh,
                 1.0f / sqrtf((float)dh));
             RET_IF(check_launch(h, "modulator_attention_kernel"));
         }
-        RET_IF(linear_f32<LIN_NONE>(h, h->mod_att, W32(h, p + "0.fn.to_out.0.weight"), W32(h, p + "0.fn.to_out.0.bias"), cur,
-                                    h->mod_y, rows, E, inner, st));
-        RET_IF(linear_f32<LIN_GELU>(h, h->mod_y, W32(h, p + "1.net.0.weight"), W32(h, p + "1.net.0.bias"), nullptr, h->mod_h,
+        RET_IF(linear_f32<LIN_NONE>(h, w.mod_att, W32(h, p + "0.fn.to_out.0.weight"), W32(h, p + "0.fn.to_out.0.bias"), cur,
+                                    w.mod_y, rows, E, inner, st));
+        RET_IF(linear_f32<LIN_GELU>(h, w.mod_y, W32(h, p + "1.net.0.weight"), W32(h, p + "1.net.0.bias"), nullptr, w.mod_h,
                                     rows, F, E, st));
-        RET_IF(linear_f32<LIN_NONE>(h, h->mod_h, W32(h, p + "1.net.3.weight"), W32(h, p + "1.net.3.bias"), h->mod_y, dst,
+        RET_IF(linear_f32<LIN_NONE>(h, w.mod_h, W32(h, p + "1.net.3.weight"), W32(h, p + "1.net.3.bias"), w.mod_y, dst,
                                     rows, E, F, st));
         cur = dst;
     }
@@ -659,7 +681,7 @@ int otam_logits(fsar_handle* h, const float* q, const float* protos, int Q, int 
 
 // Everything after the frame encoder: frame features of one episode (support rows, then target rows) -> logits,
 // class_logits.
-int head_forward(fsar_handle* h, const float* sup, const float* tgt, const float* support_labels,
+int head_forward(fsar_handle* h, HeadWs& w, const float* sup, const float* tgt, const float* support_labels,
                  const float* real_support_labels, int S, int Q, int T, int way, int merge_before, int single_direct,
                  int text_mode, float text_coff, float* logits, float* class_logits, cudaStream_t st) {
     const fsar_config& c = h->cfg;
@@ -671,13 +693,13 @@ int head_forward(fsar_handle* h, const float* sup, const float* tgt, const float
     }
     {
         Scope s(h, st, FSAR_K_HEAD_MISC, 0.0, 8.0 * S);
-        class_index_kernel<<<1, 128, 0, st>>>(support_labels, S, h->cls, h->counts, way);
+        class_index_kernel<<<1, 128, 0, st>>>(support_labels, S, w.cls, w.counts, way);
         RET_IF(check_launch(h, "class_index_kernel"));
     }
     if (text_mode == 1) {   // TRAIN.EVAL_TEXT: text probabilities only, the modulator / OTAM are not evaluated
         Scope s(h, st, FSAR_K_HEAD_MISC, 2.0 * Q * way * E, 4.0 * ((double)Q * T * E + (double)way * E));
-        text_fusion_kernel<<<Q, 256, sizeof(float) * E, st>>>(tgt, W32(h, "text_features_test"), real_support_labels, h->cls,
-                                                              h->counts, S, T, E, way, W32(h, "scale"), 1, 0.f, nullptr, logits);
+        text_fusion_kernel<<<Q, 256, sizeof(float) * E, st>>>(tgt, W32(h, "text_features_test"), real_support_labels, w.cls,
+                                                              w.counts, S, T, E, way, W32(h, "scale"), 1, 0.f, nullptr, logits);
         RET_IF(check_launch(h, "text_fusion_kernel"));
         h->last_S = S; h->last_Q = Q; h->last_T = T; h->last_way = way; h->last_rows = 0;
         h->last_sup = sup; h->last_tgt = tgt;
@@ -695,24 +717,24 @@ int head_forward(fsar_handle* h, const float* sup, const float* tgt, const float
     const int rows = Q * T + n_sup_seq * (T + 1);
     {
         Scope s(h, st, FSAR_K_HEAD_MISC, 0.0, 8.0 * rows * E);
-        build_sequences_kernel<<<rows, 128, 0, st>>>(sup, tgt, W32(h, "text_features_test"), real_support_labels, h->cls,
-                                                     h->counts, S, Q, T, E, way, merge_before, h->seq);
+        build_sequences_kernel<<<rows, 128, 0, st>>>(sup, tgt, W32(h, "text_features_test"), real_support_labels, w.cls,
+                                                     w.counts, S, Q, T, E, way, merge_before, w.seq);
         RET_IF(check_launch(h, "build_sequences_kernel"));
     }
-    // depth > 1 uses h->seq as a ping-pong buffer, so the first layer must not read it after layer 2 wrote it:
-    // layer l reads `cur` and writes dst != cur, and h->seq is only overwritten at l = 1 (after l = 0 consumed it).
-    RET_IF(modulate_rows(h, h->seq, Q, n_sup_seq, T, h->mod_out, st));
+    // depth > 1 uses w.seq as a ping-pong buffer, so the first layer must not read it after layer 2 wrote it:
+    // layer l reads `cur` and writes dst != cur, and w.seq is only overwritten at l = 1 (after l = 0 consumed it).
+    RET_IF(modulate_rows(h, w, w.seq, Q, n_sup_seq, T, w.mod_out, st));
     {
         Scope s(h, st, FSAR_K_HEAD_MISC, 0.0, 8.0 * way * T * E);
-        prototype_kernel<<<way * T, 128, 0, st>>>(h->mod_out, Q * T, n_sup_seq, T, E, h->cls, h->counts, merge_before,
-                                                  h->protos);
+        prototype_kernel<<<way * T, 128, 0, st>>>(w.mod_out, Q * T, n_sup_seq, T, E, w.cls, w.counts, merge_before,
+                                                  w.protos);
         RET_IF(check_launch(h, "prototype_kernel"));
     }
-    RET_IF(otam_logits(h, h->mod_out, h->protos, Q, way, T, single_direct, logits, h->dists, h->cum, st));
+    RET_IF(otam_logits(h, w.mod_out, w.protos, Q, way, T, single_direct, logits, w.dists, w.cum, st));
     if (text_mode == 2) {   // TRAIN.COMBINE: geometric fusion of text and visual probabilities overwrites the logits
         Scope s(h, st, FSAR_K_HEAD_MISC, 2.0 * Q * way * E, 4.0 * ((double)Q * T * E + (double)way * E));
-        text_fusion_kernel<<<Q, 256, sizeof(float) * E, st>>>(tgt, W32(h, "text_features_test"), real_support_labels, h->cls,
-                                                              h->counts, S, T, E, way, W32(h, "scale"), 2, text_coff, h->cum,
+        text_fusion_kernel<<<Q, 256, sizeof(float) * E, st>>>(tgt, W32(h, "text_features_test"), real_support_labels, w.cls,
+                                                              w.counts, S, T, E, way, W32(h, "scale"), 2, text_coff, w.cum,
                                                               logits);
         RET_IF(check_launch(h, "text_fusion_kernel"));
     }
@@ -753,15 +775,26 @@ int episodes_forward_dev(fsar_handle* h, const fsar_episode* eps, int n, float* 
         ptrs.push_back(eps[i].target_frames);  counts.push_back(eps[i].n_target * eps[i].n_frames);
     }
     RET_IF(vit_encode_segments(h, ptrs.data(), counts.data(), (int)ptrs.size(), h->feats, st));
+    // heads: tiny latency-bound kernels (~15 launches per episode). With several episodes in the call they run
+    // concurrently, one side stream per episode (fork after the encoder sweep, join before returning to `st`).
+    const bool fork = n > 1 && !h->head_streams.empty() && !h->profiling;
+    if (fork) CU_OK(h, cudaEventRecord(h->head_fork, st));
     size_t f_off = 0, l_off = 0, c_off = 0;
     for (int i = 0; i < n; ++i) {
         const fsar_episode& ep = eps[i];
         const int T = ep.n_frames;
         const float* sup = h->feats + f_off;
         const float* tgt = sup + (size_t)ep.n_support * T * E;
-        RET_IF(head_forward(h, sup, tgt, ep.support_labels, ep.real_support_labels, ep.n_support, ep.n_target, T, ep.way,
-                            ep.merge_before, ep.single_direct, ep.text_mode, ep.text_coff, logits + l_off,
-                            class_logits ? class_logits + c_off : nullptr, st));
+        cudaStream_t hs = fork ? h->head_streams[i] : st;
+        if (fork) CU_OK(h, cudaStreamWaitEvent(hs, h->head_fork, 0));
+        RET_IF(head_forward(h, h->ws[i], sup, tgt, ep.support_labels, ep.real_support_labels, ep.n_support, ep.n_target, T,
+                            ep.way, ep.merge_before, ep.single_direct, ep.text_mode, ep.text_coff, logits + l_off,
+                            class_logits ? class_logits + c_off : nullptr, hs));
+        if (fork) {
+            CU_OK(h, cudaEventRecord(h->head_done[i], hs));
+            CU_OK(h, cudaStreamWaitEvent(st, h->head_done[i], 0));
+        }
+        h->last_ws = i;
         f_off += (size_t)(ep.n_support + ep.n_target) * T * E;
         l_off += (size_t)ep.n_target * ep.way;
         c_off += (size_t)(ep.n_support + ep.n_target) * h->n_text_train;
@@ -892,9 +925,16 @@ void fsar_destroy(fsar_handle* h) {
         if (w.d16) cudaFree(w.d16);
     }
     for (float* p : h->mod_qkv) if (p) cudaFree(p);
-    void* bufs[] = {h->patches16, h->ln16, h->qkv16, h->att16, h->h16, h->x32, h->feats, h->seq, h->mod_ln, h->mod_qkvbuf,
-                    h->mod_att, h->mod_y, h->mod_h, h->mod_out, h->mod_tmp, h->protos, h->dists, h->cum, h->cls, h->counts};
+    void* bufs[] = {h->patches16, h->ln16, h->qkv16, h->att16, h->h16, h->x32, h->feats};
     for (void* p : bufs) if (p) cudaFree(p);
+    for (HeadWs& w : h->ws) {
+        void* wb[] = {w.seq, w.mod_ln, w.mod_qkvbuf, w.mod_att, w.mod_y, w.mod_h, w.mod_out, w.mod_tmp, w.protos, w.dists, w.cum,
+                      w.cls, w.counts};
+        for (void* p : wb) if (p) cudaFree(p);
+    }
+    for (cudaStream_t st : h->head_streams) if (st) cudaStreamDestroy(st);
+    for (cudaEvent_t ev : h->head_done) if (ev) cudaEventDestroy(ev);
+    if (h->head_fork) cudaEventDestroy(h->head_fork);
     for (int i = 0; i < 2; ++i) {
         HostSlot& s = h->slot[i];
         if (s.frames_dev) cudaFree(s.frames_dev);
@@ -967,7 +1007,7 @@ int fsar_modulate(fsar_handle* h, const float* x_dev, int n_seq, int n_tok, floa
     if ((size_t)n_seq * n_tok > (size_t)h->cfg.max_videos * (h->cfg.max_tokens + 1))
         return fail(h, FSAR_E_STATE, "fsar_modulate: %d x %d rows exceed the workspace", n_seq, n_tok);
     // all sequences have n_tok tokens: express as n_seq "query" sequences of T = n_tok
-    return modulate_rows(h, x_dev, n_seq, 0, n_tok, out_dev, (cudaStream_t)stream);
+    return modulate_rows(h, h->ws[0], x_dev, n_seq, 0, n_tok, out_dev, (cudaStream_t)stream);
 }
 
 int fsar_otam_logits(fsar_handle* h, const float* q_dev, const float* protos_dev, int Q, int way, int T, int single_direct,
@@ -1134,11 +1174,13 @@ int64_t fsar_peek(fsar_handle* h, const char* name, void* dst_host, int64_t nume
     const std::string n(name);
     if (n == "support_feats") { src = h->last_sup; avail = (int64_t)S * T * E; }
     else if (n == "target_feats") { src = h->last_tgt; avail = (int64_t)Q * T * E; }
-    else if (n == "mod_out") { src = h->mod_out; avail = (int64_t)h->last_rows * E; }
-    else if (n == "protos") { src = h->protos; avail = (int64_t)way * T * E; }
-    else if (n == "dists") { src = h->dists; avail = (int64_t)Q * way * T * T; }
-    else if (n == "cum_dists") { src = h->cum; avail = (int64_t)Q * way; }
-    else if (n == "class_index") { src = h->cls; avail = S; esz = sizeof(int); }
+    const HeadWs& w = h->ws[h->last_ws];
+    if (src != nullptr) {}
+    else if (n == "mod_out") { src = w.mod_out; avail = (int64_t)h->last_rows * E; }
+    else if (n == "protos") { src = w.protos; avail = (int64_t)way * T * E; }
+    else if (n == "dists") { src = w.dists; avail = (int64_t)Q * way * T * T; }
+    else if (n == "cum_dists") { src = w.cum; avail = (int64_t)Q * way; }
+    else if (n == "class_index") { src = w.cls; avail = S; esz = sizeof(int); }
     else return fail(h, FSAR_E_NAME, "unknown tap '%s'", name);
     if (numel < avail) avail = numel;
     CU_OK(h, cudaStreamSynchronize((cudaStream_t)stream));
