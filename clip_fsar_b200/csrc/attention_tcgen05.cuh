@@ -90,6 +90,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_trigger();
+    pdl_wait();
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (warp-uniform loop, elected lane)

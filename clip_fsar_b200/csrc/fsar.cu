@@ -120,6 +120,7 @@ struct fsar_handle {
     size_t l2_persist_bytes = 0, l2_window_max = 0;   // L2 set-aside for the residual stream (0 = disabled)
     bool alternate_rows = true;     // FSAR_NO_ALTERNATE=1: every kernel walks rows first-to-last (A/B testing)
     bool single_cta_gemm = false;   // FSAR_GEMM_SINGLE=1: one CTA per 128 x 256 tile instead of CTA pairs (A/B testing)
+    bool pdl = true;                // FSAR_NO_PDL=1: no programmatic dependent launch between the frame-encoder kernels
     bool legacy_attention = false;  // FSAR_LEGACY_ATTENTION=1: mma.sync attention core also for L <= 208 (A/B testing)
     std::vector<ProfRec> prof;
 };
@@ -182,6 +183,25 @@ int check_launch(fsar_handle* h, const char* what) {
     return 0;
 }
 
+// Launch of a frame-encoder kernel with programmatic dependent launch: the kernel may become resident while its
+// predecessor in `st` drains (its prologue runs early, its body waits in griddepcontrol.wait, see ptx.cuh).
+// FSAR_NO_PDL=1 launches it as an ordinary stream-ordered kernel.
+template <typename... KArgs, typename... Args>
+void launch_pdl(fsar_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = h->pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);   // errors surface in check_launch()
+}
+
 // ---------------------------------------------------------------- TMA tensor maps
 // Row-major matrix [rows, cols] (cols contiguous) of 16-bit operands (f32 == 0) or fp32 (f32 == 1),
 // box = [box_rows, box_cols] with box_cols * elem_size == 128 bytes, 128-byte swizzle.
@@ -225,7 +245,7 @@ int launch_gemm_inst(fsar_handle* h, const CUtensorMap& ta, const CUtensorMap& t
     const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (p.N + BN - 1) / BN;
     const int tiles = m_tiles * n_tiles;
     const int grid = tiles < h->sms ? tiles : h->sms;
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, p);
+    launch_pdl(h, kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, ta, tb, tc, p);
     return check_launch(h, "gemm_tn_tcgen05_kernel");
 }
 
@@ -240,7 +260,7 @@ int launch_gemm_pair_inst(fsar_handle* h, const CUtensorMap& ta, const CUtensorM
     }
     const int tiles = ((p.M + 255) / 256) * ((p.N + GEMM2_BN - 1) / GEMM2_BN);
     const int pairs = tiles < h->sms / 2 ? tiles : h->sms / 2;
-    kern<<<2 * pairs, GEMM_THREADS, GEMM2_SMEM_BYTES, st>>>(ta, tb, tc, p);   // __cluster_dims__(2, 1, 1)
+    launch_pdl(h, kern, dim3(2 * pairs), dim3(GEMM_THREADS), GEMM2_SMEM_BYTES, st, ta, tb, tc, p);   // __cluster_dims__(2, 1, 1)
     return check_launch(h, "gemm_tn_tcgen05_pair_kernel");
 }
 
@@ -318,12 +338,13 @@ int layernorm(fsar_handle* h, const float* x, void* out, const float* g, const f
     const int wpb = 8;
     const int grid = (rows + wpb - 1) / wpb;
     Scope s(h, st, cls, 0.0, (double)rows * D * (4.0 + (out16 ? 2.0 : 4.0)));
+    const float* np = nullptr;
     if (embed)
-        layernorm_kernel<T16, false, true><<<grid, 256, 0, st>>>(x, out, g, b, rows, D, 1e-5f, tokens, cls_emb, pos, reverse);
+        launch_pdl(h, layernorm_kernel<T16, false, true>, dim3(grid), dim3(256), 0, st, x, out, g, b, rows, D, 1e-5f, tokens, cls_emb, pos, reverse);
     else if (out16)
-        layernorm_kernel<T16, true, false><<<grid, 256, 0, st>>>(x, out, g, b, rows, D, 1e-5f, tokens, nullptr, nullptr, reverse);
+        launch_pdl(h, layernorm_kernel<T16, true, false>, dim3(grid), dim3(256), 0, st, x, out, g, b, rows, D, 1e-5f, tokens, np, np, reverse);
     else
-        layernorm_kernel<T16, false, false><<<grid, 256, 0, st>>>(x, out, g, b, rows, D, 1e-5f, tokens, nullptr, nullptr, reverse);
+        launch_pdl(h, layernorm_kernel<T16, false, false>, dim3(grid), dim3(256), 0, st, x, out, g, b, rows, D, 1e-5f, tokens, np, np, reverse);
     return check_launch(h, "layernorm_kernel");
 }
 
@@ -348,7 +369,7 @@ int attention(fsar_handle* h, const T16* qkv, int n_frames, int L, int heads, T1
         RET_IF(get_tmap(h, qkv, n_frames * L, 3 * D, ap.LK, 64, 0, &tkv));
         const int items = n_frames * heads;
         const int grid5 = items < h->sms ? items : h->sms;
-        attention_tcgen05_kernel<T16><<<grid5, ATT5_THREADS, ATT5_SMEM_BYTES, st>>>(tq, tkv, ap);
+        launch_pdl(h, attention_tcgen05_kernel<T16>, dim3(grid5), dim3(ATT5_THREADS), ATT5_SMEM_BYTES, st, tq, tkv, ap);
         return check_launch(h, "attention_tcgen05_kernel");
     }
     const dim3 grid((L + ATT_QROWS - 1) / ATT_QROWS, heads, n_frames);
@@ -359,7 +380,7 @@ int attention(fsar_handle* h, const T16* qkv, int n_frames, int L, int heads, T1
                                           att_smem_bytes<13>()));
             done = true;
         }
-        attention_mma_kernel<T16, 13><<<grid, 128, att_smem_bytes<13>(), st>>>(qkv, out, L, D, scale_log2e);
+        launch_pdl(h, attention_mma_kernel<T16, 13>, grid, dim3(128), att_smem_bytes<13>(), st, qkv, out, L, D, scale_log2e);
     } else if (L <= 272) {
         static bool done = false;
         if (!done) {
@@ -367,7 +388,7 @@ int attention(fsar_handle* h, const T16* qkv, int n_frames, int L, int heads, T1
                                           att_smem_bytes<17>()));
             done = true;
         }
-        attention_mma_kernel<T16, 17><<<grid, 128, att_smem_bytes<17>(), st>>>(qkv, out, L, D, scale_log2e);
+        launch_pdl(h, attention_mma_kernel<T16, 17>, grid, dim3(128), att_smem_bytes<17>(), st, qkv, out, L, D, scale_log2e);
     } else {
         return fail(h, FSAR_E_INVALID, "attention: %d tokens per frame exceeds the supported 272", L);
     }
@@ -588,9 +609,9 @@ int vit_encode_gathered(fsar_handle* h, int n, float* feats_out, cudaStream_t st
     {
         const dim3 grid((n + FINAL_FPC - 1) / FINAL_FPC, (c.embed_dim + FINAL_COLS - 1) / FINAL_COLS);
         Scope s(h, st, FSAR_K_FINAL_PROJ, 2.0 * n * D * c.embed_dim, 4.0 * ((double)D * c.embed_dim + (double)n * D));
-        final_proj_kernel<<<grid, 256, sizeof(float) * FINAL_FPC * D, st>>>(
-            h->x32, W32(h, "backbone.ln_post.weight"), W32(h, "backbone.ln_post.bias"), W32(h, "backbone.proj"),
-            feats_out, n, L, D, c.embed_dim, 1e-5f);
+        launch_pdl(h, final_proj_kernel, grid, dim3(256), sizeof(float) * FINAL_FPC * D, st,
+                   (const float*)h->x32, W32(h, "backbone.ln_post.weight"), W32(h, "backbone.ln_post.bias"), W32(h, "backbone.proj"),
+                   feats_out, n, L, D, c.embed_dim, 1e-5f);
         RET_IF(check_launch(h, "final_proj_kernel"));
     }
     set_l2_window(h, st, nullptr, 0);
@@ -603,8 +624,8 @@ int patch_gather(fsar_handle* h, const float* frames, int n, int row_frame_offse
     const long long total = (long long)n * 3 * S * G;
     const int grid = (int)((total + 255) / 256);
     Scope s(h, st, FSAR_K_PATCH_GATHER, 0.0, (double)n * 3 * S * S * 6.0);
-    patch_gather_kernel<T16><<<grid, 256, 0, st>>>(frames, h->patches16 + (size_t)row_frame_offset * G * G * h->patch_kp,
-                                                   n, S, P, h->patch_kp);
+    launch_pdl(h, patch_gather_kernel<T16>, dim3(grid), dim3(256), 0, st, frames,
+               h->patches16 + (size_t)row_frame_offset * G * G * h->patch_kp, n, S, P, h->patch_kp);
     return check_launch(h, "patch_gather_kernel");
 }
 
@@ -877,6 +898,8 @@ int fsar_create(const fsar_config* cfg, fsar_handle** out) {
         h->alternate_rows = !(e != nullptr && e[0] == '1');
         e = getenv("FSAR_GEMM_SINGLE");
         h->single_cta_gemm = (e != nullptr && e[0] == '1');
+        e = getenv("FSAR_NO_PDL");
+        h->pdl = !(e != nullptr && e[0] == '1');
     }
     int rc = 0;
     do {

@@ -80,6 +80,8 @@ gemm_tn_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     cluster_sync_all();   // barrier inits of both CTAs are visible before any remote arrive / TMA completion
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_trigger();   // the next kernel of the stream may set itself up while this grid runs ...
+    pdl_wait();      // ... and this one touches global memory only after its predecessor has completed
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (both CTAs; warp-uniform loop)

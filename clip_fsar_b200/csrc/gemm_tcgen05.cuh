@@ -254,6 +254,8 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_trigger();
+    pdl_wait();
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer

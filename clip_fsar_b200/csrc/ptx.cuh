@@ -30,6 +30,15 @@ __device__ __forceinline__ bool elect_one() {
 // in uniform registers instead of wrapping each TMA / MMA issue in an R2UR broadcast loop).
 __device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0); }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still draining: everything up to pdl_wait() (barrier init, TMEM allocation, tensor-map prefetch) overlaps
+// the predecessor's tail; pdl_wait() returns once the predecessor grid has completed and its writes are visible.
+// pdl_trigger() lets the successor of THIS kernel be scheduled as soon as every CTA of this grid has issued it
+// (it still blocks in its own pdl_wait() until this grid is complete). Both are no-ops in a normal launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -60,6 +60,8 @@ preprocess_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, c
 template <typename T16>
 __global__ void patch_gather_kernel(const float* __restrict__ frames, T16* __restrict__ out, int n_frames, int S,
                                     int P, int Kp) {
+    pdl_trigger();
+    pdl_wait();
     const int G = S / P;
     const long long total = (long long)n_frames * 3 * S * G;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -104,6 +106,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x, void* out, const float* __restrict__ gamma, const float* __restrict__ beta,
                  int rows, int D, float eps, int tokens, const float* __restrict__ cls_emb,
                  const float* __restrict__ pos, int reverse) {
+    pdl_trigger();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int row = blockIdx.x * (blockDim.x >> 5) + warp;
     if (row >= rows) return;
@@ -181,6 +185,8 @@ final_proj_kernel(const float* __restrict__ x, const float* __restrict__ gamma, 
                   float eps) {
     extern __shared__ float sm[];  // [FPC][D]
     __shared__ float red[2][FINAL_FPC][8];
+    pdl_trigger();
+    pdl_wait();
     const int f0 = blockIdx.x * FINAL_FPC;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // load CLS rows
@@ -312,6 +318,8 @@ attention_mma_kernel(const T16* __restrict__ qkv, T16* __restrict__ out, int L, 
     T16* sV = sK + LP * ATT_PITCH;
     T16* sQ = sV + LP * ATT_PITCH;
 
+    pdl_trigger();
+    pdl_wait();
     const int qblk = blockIdx.x, head = blockIdx.y, frame = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t row0 = (size_t)frame * L;
