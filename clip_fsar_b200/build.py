@@ -11,6 +11,7 @@ DEPS = sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HER
 
 
 OUT_BF16 = os.path.join(HERE, "libfsar_sm100_bf16.so")
+OUT_PROBES = os.path.join(HERE, "libfsar_sm100_probes.so")   # -DFSAR_PROBES: bottleneck probes for tools/gemm_probe.py
 
 
 def nvcc_cmd(extra=(), out=OUT):
@@ -26,15 +27,17 @@ def up_to_date(out=OUT):
     return all(os.path.getmtime(d) <= t for d in DEPS)
 
 
-def build(force=False, verbose=False, bf16=False):
+def build(force=False, verbose=False, bf16=False, probes=False):
     """fp16 operands (default, libfsar_sm100.so) or bf16 operands (libfsar_sm100_bf16.so, select it with
     FSAR_LIB_PATH). Same sources, -DFSAR_BF16 switches the operand type of every 16-bit buffer."""
-    out = OUT_BF16 if bf16 else OUT
+    out = OUT_PROBES if probes else (OUT_BF16 if bf16 else OUT)
     if not force and up_to_date(out):
         return out
     extra = ["-Xptxas", "-v"] if verbose else []
     if bf16:
         extra.append("-DFSAR_BF16")
+    if probes:
+        extra.append("-DFSAR_PROBES")
     r = subprocess.run(nvcc_cmd(extra, out), capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
@@ -45,4 +48,4 @@ def build(force=False, verbose=False, bf16=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, bf16="--bf16" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, bf16="--bf16" in sys.argv, probes="--probes" in sys.argv))

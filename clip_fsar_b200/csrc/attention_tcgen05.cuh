@@ -46,6 +46,8 @@ struct Att5Params {
     float scale_log2e;
     void* out;       // [n_frames * L, D] 16-bit
     int reverse;     // walk the (frame, head) items last-to-first (L2 reuse of the QKV rows written last)
+    int debug;       // only read by the -DFSAR_PROBES build (tools/gemm_probe.py, results WRONG): 1 skip the max pass,
+                     // 2 no exp2, 4 no stores
 };
 
 template <typename T16>
@@ -178,7 +180,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                 if (warp_valid) {
                     // ---- pass 1: row maximum (only the last chunk can contain padded keys >= L)
                     float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-                    for (int c = 0; c < n32; ++c) {
+                    if (FSAR_PROBE(p.debug, 1)) mx0 = 0.f;
+                    for (int c = 0; c < (FSAR_PROBE(p.debug, 1) ? 0 : n32); ++c) {
                         uint32_t r[32];
                         tmem_ld_32x32b_x32(t_row + c * 32, r);
                         tc_wait_ld();
@@ -197,7 +200,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                                 if (j < lim) mx0 = fmaxf(mx0, __uint_as_float(r[j]));
                         }
                     }
-                    if (tail16) {
+                    if (tail16 && !FSAR_PROBE(p.debug, 1)) {
                         uint32_t r[16];
                         tmem_ld_32x32b_x16(t_row + n32 * 32, r);
                         tc_wait_ld();
@@ -214,7 +217,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                         tmem_ld_32x32b_x32(t_row + c * 32, r);
                         tc_wait_ld();
                         const int lim = p.L - c * 32;
-                        if (lim >= 32) {
+                        if (FSAR_PROBE(p.debug, 2)) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) w[j] = r[2 * j];
+                        } else if (lim >= 32) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 const float e0 = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2e, -m_scaled));
@@ -268,7 +274,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&o_empty[g]);
-                if (valid) {
+                if (valid && !FSAR_PROBE(p.debug, 4)) {
                     const float inv = 1.0f / sum;
                     uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)frame * p.L + row) * p.D + head * 64);
 #pragma unroll

@@ -120,6 +120,7 @@ struct fsar_handle {
     size_t l2_persist_bytes = 0, l2_window_max = 0;   // L2 set-aside for the residual stream (0 = disabled)
     bool alternate_rows = true;     // FSAR_NO_ALTERNATE=1: every kernel walks rows first-to-last (A/B testing)
     bool single_cta_gemm = false;   // FSAR_GEMM_SINGLE=1: one CTA per 128 x 256 tile instead of CTA pairs (A/B testing)
+    int gemm_debug = 0;             // FSAR_GEMM_DEBUG: bottleneck probes, -DFSAR_PROBES build only (tools/gemm_probe.py)
     bool pdl = true;                // FSAR_NO_PDL=1: no programmatic dependent launch between the frame-encoder kernels
     bool legacy_attention = false;  // FSAR_LEGACY_ATTENTION=1: mma.sync attention core also for L <= 208 (A/B testing)
     std::vector<ProfRec> prof;
@@ -295,7 +296,7 @@ int gemm(fsar_handle* h, int cls, const T16* a, const T16* w, const float* bias,
     if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out)) & 15)
         return fail(h, FSAR_E_INVALID, "gemm: operands must be 16-byte aligned");
     GemmParams p{};
-    p.M = M; p.N = N; p.K = K; p.bias = bias; p.reverse = reverse;
+    p.M = M; p.N = N; p.K = K; p.bias = bias; p.reverse = reverse; p.debug = h->gemm_debug;
     const int bn = (N >= 256) ? 256 : ((N >= 128) ? 128 : 64);
     const bool out16 = (epi == EPI_STORE16 || epi == EPI_QGELU16);
     CUtensorMap ta, tb, tc;
@@ -364,6 +365,7 @@ int attention(fsar_handle* h, const T16* qkv, int n_frames, int L, int heads, T1
         Att5Params ap{};
         ap.n_frames = n_frames; ap.L = L; ap.heads = heads; ap.D = D;
         ap.LK = round_up(L, 16); ap.n_mtiles = (L + 127) / 128; ap.scale_log2e = scale_log2e; ap.out = out; ap.reverse = reverse;
+        { const char* e = getenv("FSAR_ATT_DEBUG"); ap.debug = e ? atoi(e) : 0; }
         CUtensorMap tq, tkv;
         RET_IF(get_tmap(h, qkv, n_frames * L, 3 * D, 128, 64, 0, &tq));
         RET_IF(get_tmap(h, qkv, n_frames * L, 3 * D, ap.LK, 64, 0, &tkv));
@@ -898,6 +900,8 @@ int fsar_create(const fsar_config* cfg, fsar_handle** out) {
         h->alternate_rows = !(e != nullptr && e[0] == '1');
         e = getenv("FSAR_GEMM_SINGLE");
         h->single_cta_gemm = (e != nullptr && e[0] == '1');
+        e = getenv("FSAR_GEMM_DEBUG");
+        h->gemm_debug = e != nullptr ? atoi(e) : 0;
         e = getenv("FSAR_NO_PDL");
         h->pdl = !(e != nullptr && e[0] == '1');
     }

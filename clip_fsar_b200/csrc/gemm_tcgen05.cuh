@@ -34,7 +34,15 @@ struct GemmParams {
     const float* bias;  // [N] or nullptr
     int reverse;        // walk the row blocks last-to-first: a consumer that reads its producer's output in the opposite
                         // order finds the most recently written rows still in L2 (LRU), see fsar.cu
+    int debug;          // only read by the -DFSAR_PROBES build (tools/gemm_probe.py; results are WRONG when set):
+                        // 1 = epilogue drains TMEM but stores nothing, 2 = epilogue releases the accumulator without
+                        // reading it, 4 = smem staging without the TMA store, 8 = every tile is stored over row block 0
 };
+#ifdef FSAR_PROBES
+#define FSAR_PROBE(flags, bit) (((flags) & (bit)) != 0)
+#else
+#define FSAR_PROBE(flags, bit) false
+#endif
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 x 2 B = 128 B = one swizzle-128B row
@@ -116,6 +124,12 @@ __device__ __forceinline__ void gemm_epilogue_tile(uint32_t t_base, int row0, in
     constexpr int CHUNK = kOut16 ? 64 : 32;
     constexpr int NCH = BN / CHUNK;
     bool released = false;
+    if (FSAR_PROBE(p.debug, 2)) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) release();
+        return;
+    }
 
 #pragma unroll 1
     for (int c = half; c < NCH; c += 2) {
@@ -177,6 +191,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(uint32_t t_base, int row0, in
                 }
             }
         }
+        if (FSAR_PROBE(p.debug, 1)) continue;
         // the staging buffer must have been drained by the previous TMA store of this warp
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
@@ -185,9 +200,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(uint32_t t_base, int row0, in
             st_shared_v4(row_addr + ((uint32_t(j) ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0 && row0 < p.M && col0 < p.N) {
-            if (EPI == EPI_RESID32) tma_reduce_add_2d(tmC, stage_ptr, col0, row0);
-            else tma_store_2d(tmC, stage_ptr, col0, row0);
+        if (lane == 0 && row0 < p.M && col0 < p.N && !FSAR_PROBE(p.debug, 4)) {
+            const int r_st = FSAR_PROBE(p.debug, 8) ? (row0 & 255) : row0;
+            if (EPI == EPI_RESID32) tma_reduce_add_2d(tmC, stage_ptr, col0, r_st);
+            else tma_store_2d(tmC, stage_ptr, col0, r_st);
             tma_store_commit();
         }
     }
