@@ -50,7 +50,9 @@ struct Att5Params {
                      // 2 no exp2, 4 no stores
 };
 
-template <typename T16>
+// CAUSAL: query token i attends to keys 0..i only (the additive -inf upper-triangular mask of the CLIP text transformer,
+// few_shot.py:777-783); the frame encoder uses CAUSAL = false.
+template <typename T16, bool CAUSAL>
 __global__ void __launch_bounds__(ATT5_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                          const Att5Params p) {
@@ -165,6 +167,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             const int row = g * 128 + wq * 32 + lane;     // query token of this thread
             const bool warp_valid = (g * 128 + wq * 32) < p.L;
             const bool valid = row < p.L;
+            const int n_keys = (CAUSAL && row + 1 < p.L) ? row + 1 : p.L;   // keys this query row may attend to
             const uint32_t t_row = tmem_base + g * 256 + (uint32_t(wq * 32) << 16);
             const int n32 = p.LK / 32;             // full 32-column chunks of the score row
             const bool tail16 = (p.LK & 16) != 0;  // plus one 16-column chunk
@@ -185,7 +188,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                         uint32_t r[32];
                         tmem_ld_32x32b_x32(t_row + c * 32, r);
                         tc_wait_ld();
-                        const int lim = p.L - c * 32;
+                        const int lim = n_keys - c * 32;
                         if (lim >= 32) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
@@ -204,7 +207,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                         uint32_t r[16];
                         tmem_ld_32x32b_x16(t_row + n32 * 32, r);
                         tc_wait_ld();
-                        const int lim = p.L - n32 * 32;
+                        const int lim = n_keys - n32 * 32;
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
                             if (j < lim) mx1 = fmaxf(mx1, __uint_as_float(r[j]));
@@ -216,7 +219,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                         uint32_t r[32], w[16];
                         tmem_ld_32x32b_x32(t_row + c * 32, r);
                         tc_wait_ld();
-                        const int lim = p.L - c * 32;
+                        const int lim = n_keys - c * 32;
                         if (FSAR_PROBE(p.debug, 2)) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) w[j] = r[2 * j];
@@ -246,7 +249,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                         uint32_t r[16], w[8];
                         tmem_ld_32x32b_x16(t_row + n32 * 32, r);
                         tc_wait_ld();
-                        const int lim = p.L - n32 * 32;
+                        const int lim = n_keys - n32 * 32;
 #pragma unroll
                         for (int j = 0; j < 16; j += 2) {
                             const float e0 = (j < lim) ? ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2e, -m_scaled)) : 0.f;

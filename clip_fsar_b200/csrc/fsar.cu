@@ -24,6 +24,7 @@
 #include "gemm_pair_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
 #include "head_kernels.cuh"
+#include "text_kernels.cuh"
 #include "vit_kernels.cuh"
 
 using namespace fsar;
@@ -48,7 +49,8 @@ struct Weight {
     int rows = 0, cols = 0, kp = 0;
     bool owns32 = true;
     bool set = false;
-    bool required = true;
+    bool required = true;  // false: text_features_{train,test} (needed by episodes only) and the optional text tower
+    bool tower = false;    // true: a weight of the CLIP text tower ("clip.*", registered by fsar_text_configure)
 };
 
 // Workspace of one episode's head (modulator, prototypes, cos/OTAM). One per episode slot of a batched call, so the
@@ -90,6 +92,7 @@ struct fsar_handle {
     std::unordered_map<std::string, int> widx;
     std::vector<std::string> missing_cache;
     int n_text_train = 0, n_text_test = 0;
+    fsar_text_config text_cfg = {0, 0, 0, 0, 0};   // width == 0: no text tower configured
     // fused modulator QKV weights: one [3 * inner, E] allocation per layer
     std::vector<float*> mod_qkv;
     // ---- ViT workspace (capacity cfg.max_frames)
@@ -349,16 +352,21 @@ int layernorm(fsar_handle* h, const float* x, void* out, const float* g, const f
     return check_launch(h, "layernorm_kernel");
 }
 
-int attention(fsar_handle* h, const T16* qkv, int n_frames, int L, int heads, T16* out, cudaStream_t st, int reverse = 0) {
+int attention(fsar_handle* h, const T16* qkv, int n_frames, int L, int heads, T16* out, cudaStream_t st, int reverse = 0,
+              int causal = 0) {
     const int D = heads * ATT_HD;
     const float scale_log2e = 0.125f * 1.4426950408889634f;  // head_dim ** -0.5 * log2(e)
     Scope s(h, st, FSAR_K_ATTENTION, 4.0 * n_frames * heads * (double)L * L * ATT_HD,
             (double)n_frames * L * D * 2.0 * 4.0);
-    if (L <= ATT5_MAX_KEYS && !h->legacy_attention) {
+    if (causal && L > ATT5_MAX_KEYS)
+        return fail(h, FSAR_E_INVALID, "causal attention supports at most %d tokens, got %d", ATT5_MAX_KEYS, L);
+    if (L <= ATT5_MAX_KEYS && (!h->legacy_attention || causal)) {
         // tcgen05 / TMEM path: S and O accumulate in tensor memory, one softmax thread per query row
         static bool done5 = false;
         if (!done5) {
-            CU_OK(h, cudaFuncSetAttribute(attention_tcgen05_kernel<T16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            CU_OK(h, cudaFuncSetAttribute(attention_tcgen05_kernel<T16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          ATT5_SMEM_BYTES));
+            CU_OK(h, cudaFuncSetAttribute(attention_tcgen05_kernel<T16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           ATT5_SMEM_BYTES));
             done5 = true;
         }
@@ -371,7 +379,10 @@ int attention(fsar_handle* h, const T16* qkv, int n_frames, int L, int heads, T1
         RET_IF(get_tmap(h, qkv, n_frames * L, 3 * D, ap.LK, 64, 0, &tkv));
         const int items = n_frames * heads;
         const int grid5 = items < h->sms ? items : h->sms;
-        launch_pdl(h, attention_tcgen05_kernel<T16>, dim3(grid5), dim3(ATT5_THREADS), ATT5_SMEM_BYTES, st, tq, tkv, ap);
+        if (causal)
+            launch_pdl(h, attention_tcgen05_kernel<T16, true>, dim3(grid5), dim3(ATT5_THREADS), ATT5_SMEM_BYTES, st, tq, tkv, ap);
+        else
+            launch_pdl(h, attention_tcgen05_kernel<T16, false>, dim3(grid5), dim3(ATT5_THREADS), ATT5_SMEM_BYTES, st, tq, tkv, ap);
         return check_launch(h, "attention_tcgen05_kernel");
     }
     const dim3 grid((L + ATT_QROWS - 1) / ATT_QROWS, heads, n_frames);
@@ -423,6 +434,8 @@ void add_w(fsar_handle* h, const std::string& name, int64_t numel, int rows = 0,
     h->w.push_back(w);
 }
 
+int alloc_weight_storage(fsar_handle* h);
+
 int alloc_weights(fsar_handle* h) {
     const fsar_config& c = h->cfg;
     const int D = c.width, E = c.embed_dim, P = c.patch_size;
@@ -471,7 +484,14 @@ int alloc_weights(fsar_handle* h) {
     h->mod_qkv.assign(c.mod_depth, nullptr);
     for (int l = 0; l < c.mod_depth; ++l)
         CU_OK(h, cudaMalloc(&h->mod_qkv[l], sizeof(float) * 3 * (size_t)inner * E));
+    return alloc_weight_storage(h);
+}
+
+int alloc_weight_storage(fsar_handle* h) {
+    const fsar_config& c = h->cfg;
+    const int E = c.embed_dim, inner = c.mod_heads * c.mod_dim_head;
     for (auto& w : h->w) {
+        if (w.d32 != nullptr) continue;   // already allocated (fsar_text_configure calls this again)
         // the three modulator projections of a layer live in one [3 * inner, E] buffer (one fused launch)
         size_t pos;
         int which = -1;
@@ -542,7 +562,7 @@ int alloc_workspace(fsar_handle* h) {
 
 bool ready(fsar_handle* h, bool need_text) {
     for (auto& w : h->w)
-        if (!w.set && (w.required || need_text)) return false;
+        if (!w.set && !w.tower && (w.required || need_text)) return false;
     return true;
 }
 
@@ -985,7 +1005,7 @@ int fsar_set_weight(fsar_handle* h, const char* name, const float* data, int64_t
     Weight* w = find_w(h, name);
     if (w == nullptr) return fail(h, FSAR_E_NAME, "unknown weight '%s'", name);
     const int E = h->cfg.embed_dim;
-    const bool is_text = !w->required;
+    const bool is_text = !w->required && !w->tower;   // text_features_{train,test}: any number of rows up to max_classes
     if (is_text) {
         if (numel <= 0 || numel % E != 0 || numel > w->numel)
             return fail(h, FSAR_E_INVALID, "%s: numel %lld must be a multiple of embed_dim %d and <= %lld", name,
@@ -1178,6 +1198,93 @@ int fsar_episodes_submit_host_u8(fsar_handle* h, int slot, const fsar_episode* e
     CU_OK(h, cudaMemcpyAsync(s.clogits_pin, s.clogits_dev, sizeof(float) * n_clogits, cudaMemcpyDeviceToHost, h->compute_stream));
     CU_OK(h, cudaEventRecord(s.done, h->compute_stream));
     s.n_logits = n_logits; s.n_clogits = n_clogits; s.busy = 1;
+    return 0;
+}
+
+int fsar_text_configure(fsar_handle* h, const fsar_text_config* tc) {
+    if (h == nullptr || tc == nullptr) return fail(h, FSAR_E_INVALID, "fsar_text_configure: NULL argument");
+    if (h->text_cfg.width != 0) return fail(h, FSAR_E_STATE, "the text tower is already configured");
+    if (tc->width % 128 != 0 || tc->width > 1024 || tc->heads * ATT_HD != tc->width || tc->layers < 1 ||
+        tc->context_length < 1 || tc->context_length > ATT5_MAX_KEYS || tc->vocab_size < 1)
+        return fail(h, FSAR_E_INVALID, "unsupported text tower (width %d, heads %d, layers %d, context %d, vocab %d)",
+                    tc->width, tc->heads, tc->layers, tc->context_length, tc->vocab_size);
+    CU_OK(h, cudaSetDevice(h->cfg.device));
+    const int W = tc->width, E = h->cfg.embed_dim;
+    const size_t first = h->w.size();
+    add_w(h, "clip.token_embedding.weight", (int64_t)tc->vocab_size * W, 0, 0, 0, false);
+    add_w(h, "clip.positional_embedding", (int64_t)tc->context_length * W, 0, 0, 0, false);
+    add_w(h, "clip.ln_final.weight", W, 0, 0, 0, false);
+    add_w(h, "clip.ln_final.bias", W, 0, 0, 0, false);
+    add_w(h, "clip.text_projection", (int64_t)W * E, 0, 0, 0, false);
+    for (int i = 0; i < tc->layers; ++i) {
+        const std::string p = "clip.transformer.resblocks." + std::to_string(i) + ".";
+        add_w(h, p + "attn.in_proj_weight", (int64_t)3 * W * W, 3 * W, W, W, false);
+        add_w(h, p + "attn.in_proj_bias", 3 * W, 0, 0, 0, false);
+        add_w(h, p + "attn.out_proj.weight", (int64_t)W * W, W, W, W, false);
+        add_w(h, p + "attn.out_proj.bias", W, 0, 0, 0, false);
+        add_w(h, p + "ln_1.weight", W, 0, 0, 0, false);
+        add_w(h, p + "ln_1.bias", W, 0, 0, 0, false);
+        add_w(h, p + "ln_2.weight", W, 0, 0, 0, false);
+        add_w(h, p + "ln_2.bias", W, 0, 0, 0, false);
+        add_w(h, p + "mlp.c_fc.weight", (int64_t)4 * W * W, 4 * W, W, W, false);
+        add_w(h, p + "mlp.c_fc.bias", 4 * W, 0, 0, 0, false);
+        add_w(h, p + "mlp.c_proj.weight", (int64_t)4 * W * W, W, 4 * W, 4 * W, false);
+        add_w(h, p + "mlp.c_proj.bias", W, 0, 0, 0, false);
+    }
+    for (size_t i = first; i < h->w.size(); ++i) h->w[i].tower = true;
+    RET_IF(alloc_weight_storage(h));
+    h->text_cfg = *tc;
+    return 0;
+}
+
+int fsar_text_encode(fsar_handle* h, const int32_t* tokens_dev, int n_texts, float* out_dev, void* stream) {
+    if (h == nullptr || tokens_dev == nullptr || out_dev == nullptr || n_texts < 1)
+        return fail(h, FSAR_E_INVALID, "fsar_text_encode: bad argument");
+    const fsar_text_config& t = h->text_cfg;
+    if (t.width == 0) return fail(h, FSAR_E_STATE, "fsar_text_encode: call fsar_text_configure first");
+    for (auto& w : h->w)
+        if (w.tower && !w.set) return fail(h, FSAR_E_STATE, "text tower weight '%s' has not been set", w.name.c_str());
+    cudaStream_t st = (cudaStream_t)stream;
+    const int W = t.width, C = t.context_length, E = h->cfg.embed_dim;
+    // the blocks run in the frame encoder's workspace (x32 / ln16 / qkv16 / att16 / h16 hold max_frames * tokens rows of
+    // `width` columns); texts are encoded in chunks that fit
+    const size_t cap_rows = (size_t)h->cfg.max_frames * h->tokens * h->cfg.width / W;
+    const int chunk = (int)(cap_rows / C);
+    if (chunk < 1) return fail(h, FSAR_E_STATE, "workspace too small for one text of %d tokens (raise max_frames)", C);
+    for (int done = 0; done < n_texts; done += chunk) {
+        const int n = n_texts - done < chunk ? n_texts - done : chunk;
+        const int M = n * C;
+        const int* tok = tokens_dev + (size_t)done * C;
+        {
+            Scope s(h, st, FSAR_K_HEAD_MISC, 0.0, 12.0 * M * W);
+            text_embed_kernel<<<(M + 7) / 8, 256, 0, st>>>(tok, W32(h, "clip.token_embedding.weight"),
+                                                           W32(h, "clip.positional_embedding"), h->x32, M, C, W, t.vocab_size);
+            RET_IF(check_launch(h, "text_embed_kernel"));
+        }
+        for (int i = 0; i < t.layers; ++i) {
+            const std::string pre = "clip.transformer.resblocks." + std::to_string(i) + ".";
+            RET_IF(layernorm(h, h->x32, h->ln16, W32(h, pre + "ln_1.weight"), W32(h, pre + "ln_1.bias"), M, W, true, false, C,
+                             nullptr, nullptr, st, FSAR_K_LAYERNORM));
+            RET_IF(gemm(h, FSAR_K_GEMM_QKV, h->ln16, W16(h, pre + "attn.in_proj_weight"), W32(h, pre + "attn.in_proj_bias"),
+                        h->qkv16, M, 3 * W, W, EPI_STORE16, st));
+            RET_IF(attention(h, h->qkv16, n, C, t.heads, h->att16, st, 0, /*causal=*/1));
+            RET_IF(gemm(h, FSAR_K_GEMM_OUT, h->att16, W16(h, pre + "attn.out_proj.weight"), W32(h, pre + "attn.out_proj.bias"),
+                        h->x32, M, W, W, EPI_RESID32, st));
+            RET_IF(layernorm(h, h->x32, h->ln16, W32(h, pre + "ln_2.weight"), W32(h, pre + "ln_2.bias"), M, W, true, false, C,
+                             nullptr, nullptr, st, FSAR_K_LAYERNORM));
+            RET_IF(gemm(h, FSAR_K_GEMM_FC1, h->ln16, W16(h, pre + "mlp.c_fc.weight"), W32(h, pre + "mlp.c_fc.bias"), h->h16, M,
+                        4 * W, W, EPI_QGELU16, st));
+            RET_IF(gemm(h, FSAR_K_GEMM_FC2, h->h16, W16(h, pre + "mlp.c_proj.weight"), W32(h, pre + "mlp.c_proj.bias"), h->x32,
+                        M, W, 4 * W, EPI_RESID32, st));
+        }
+        {
+            Scope s(h, st, FSAR_K_FINAL_PROJ, 2.0 * n * W * E, 4.0 * ((double)W * E + (double)n * W));
+            text_final_kernel<<<n, 256, sizeof(float) * W, st>>>(h->x32, tok, W32(h, "clip.ln_final.weight"),
+                                                                 W32(h, "clip.ln_final.bias"), W32(h, "clip.text_projection"),
+                                                                 out_dev + (size_t)done * E, C, W, E, 1e-5f);
+            RET_IF(check_launch(h, "text_final_kernel"));
+        }
+    }
     return 0;
 }
 

@@ -9,6 +9,10 @@ stream. There is no torch / CPU fallback: forward on a machine without an sm_100
 Scope: the eval forward (few_shot.py:2834-2990) — the visual else-branch honouring
 TRAIN.MERGE_BEFORE, TRAIN.SINGLE_DIRECT, TRAIN.TRANSFORMER_DEPTH and DATA.NUM_INPUT_FRAMES, and the text branches
 TRAIN.EVAL_TEXT / TRAIN.COMBINE (+ TEXT_COFF). Training mode raises NotImplementedError.
+
+text_features_{train,test} (few_shot.py:2714-2728): given a CLIP checkpoint (VIDEO.HEAD.CLIP_CHECKPOINT) the class
+prompts are tokenised on the host (the reference's own BPE tokenizer) and encoded by the library's text tower
+(fsar_text_encode) on first use; otherwise they are passed in / loaded from a .pt file.
 """
 import os
 import warnings
@@ -102,7 +106,7 @@ class CNN_OTAM_CLIPFSAR_SM100(nn.Module):
     """B200 (sm_100a) implementation of CNN_OTAM_CLIPFSAR's inference forward. Register with
     `clip_fsar_b200.register.register()` and select with `VIDEO.HEAD.NAME: CNN_OTAM_CLIPFSAR_SM100`."""
 
-    def __init__(self, cfg, text_features_train=None, text_features_test=None):
+    def __init__(self, cfg, text_features_train=None, text_features_test=None, tokenizer=None):
         super().__init__()
         self.args = cfg
         name = cfg.VIDEO.HEAD.BACKBONE_NAME
@@ -129,15 +133,21 @@ class CNN_OTAM_CLIPFSAR_SM100(nn.Module):
         self._init_parameters()
 
         head_cfg = cfg.VIDEO.HEAD
+        self._text_state = None          # text side of the CLIP checkpoint, encoded on the device at first use
+        self._text_tokens = None
         ckpt = _cfg_get(head_cfg, "CLIP_CHECKPOINT", None)
         if ckpt:
-            self.load_clip_visual(ckpt)
-        # text_features_{train,test}: plain attributes, not buffers (few_shot.py:2720, 2728). The CLIP text tower
-        # that produces them is init-time only and out of scope: they are an input here.
+            self._text_state = self.load_clip_visual(ckpt)
+        # text_features_{train,test}: plain attributes, not buffers (few_shot.py:2720, 2728)
         tf_path = _cfg_get(head_cfg, "TEXT_FEATURES", None)
         if text_features_train is None and tf_path:
             blob = torch.load(tf_path, map_location="cpu")
             text_features_train, text_features_test = blob["train"], blob["test"]
+        if text_features_train is None and self._text_state:
+            # few_shot.py:2714-2728: tokenize(prompt.format(class)) -> encode_text, with the library's text tower
+            self.set_clip_text(self._text_state, tokenizer, _cfg_get(cfg.TEST, "PROMPT", None))
+            text_features_train = torch.zeros(len(self.class_real_train), self.mid_dim)     # placeholders until the
+            text_features_test = torch.zeros(len(self.class_real_test), self.mid_dim)       # first forward on a GPU
         if text_features_train is None:
             if not _cfg_get(head_cfg, "SYNTHETIC_TEXT", False):
                 raise ValueError("text features are required: pass text_features_train/test, or set VIDEO.HEAD."
@@ -172,7 +182,8 @@ class CNN_OTAM_CLIPFSAR_SM100(nn.Module):
                     p.normal_(0.0, fan_in ** -0.5)
 
     def load_clip_visual(self, path):
-        """Fill `backbone.*` from an OpenAI CLIP checkpoint (state_dict or TorchScript archive): keys 'visual.*'."""
+        """Fill `backbone.*` from an OpenAI CLIP checkpoint (state_dict or TorchScript archive): keys 'visual.*'.
+        Returns the text side of the checkpoint (CLIP.encode_text's parameters) or None if it has none."""
         try:
             sd = torch.jit.load(path, map_location="cpu").state_dict()
         except RuntimeError:
@@ -182,6 +193,31 @@ class CNN_OTAM_CLIPFSAR_SM100(nn.Module):
         missing = self.backbone.load_state_dict(vis, strict=False)
         if missing.missing_keys:
             raise ValueError("CLIP checkpoint %s lacks visual keys: %s" % (path, missing.missing_keys[:5]))
+        text = {k: v.float() for k, v in sd.items() if torch.is_tensor(v) and v.dim() > 0 and not k.startswith("visual.")}
+        return text if "token_embedding.weight" in text else None
+
+    def set_clip_text(self, clip_text_state, tokenizer=None, prompt=None):
+        """Have text_features_{train,test} computed by the library's CLIP text tower from `clip_text_state` (the
+        non-visual tensors of a CLIP state_dict) at the next forward. Prompts as in few_shot.py:2714-2727:
+        TEST.PROMPT.format(name) or "a photo of {name}". `tokenizer(list[str]) -> int [n, 77]` defaults to the
+        reference's tokenize (few_shot.py:393-429; importable once clip_fsar_b200.register.register() ran)."""
+        if tokenizer is None:
+            try:
+                from models.base.few_shot import tokenize as tokenizer
+            except ImportError as e:
+                raise ImportError("no tokenizer: pass tokenizer=, or make the reference tree importable "
+                                  "(clip_fsar_b200.register.register())") from e
+        fmt = prompt if prompt else "a photo of {}"
+        self._text_tokens = tuple(torch.as_tensor(tokenizer([fmt.format(n) for n in names])).to(torch.int32)
+                                  for names in (self.class_real_train, self.class_real_test))
+        W = clip_text_state["ln_final.weight"].shape[0]
+        layers = 1 + max(int(k.split(".")[2]) for k in clip_text_state if k.startswith("transformer.resblocks."))
+        self._text_geometry = dict(width=W, layers=layers, heads=W // 64,
+                                   context_length=clip_text_state["positional_embedding"].shape[0],
+                                   vocab_size=clip_text_state["token_embedding.weight"].shape[0])
+        self._text_state = {k: v for k, v in clip_text_state.items() if k != "logit_scale"}
+        self._text_pending = True
+        self._mark_dirty()
 
     def _mark_dirty(self):
         self._pushed_versions = None
@@ -190,6 +226,7 @@ class CNN_OTAM_CLIPFSAR_SM100(nn.Module):
         """Replace text_features_{train,test} ([n_cls, embed_dim] fp32; few_shot.py:2720, 2728)."""
         self.text_features_train = torch.as_tensor(train, dtype=torch.float32)
         self.text_features_test = torch.as_tensor(test, dtype=torch.float32)
+        self._text_tokens, self._text_pending = None, False        # explicit features replace the text tower's
         if self._engine is not None and max(self.text_features_train.shape[0], self.text_features_test.shape[0]) \
                 > self._engine.cfg.max_classes:
             self._engine.close()
@@ -207,6 +244,17 @@ class CNN_OTAM_CLIPFSAR_SM100(nn.Module):
             g.update(max_frames=min(cap * self.num_frames, 384), max_videos=cap, max_tokens=self.num_frames,
                      max_classes=n_cls, otam_lambda=0.5, device=device.index if device.index is not None else 0)
             self._engine = _lib.Engine(**g)
+            self._pushed_versions = None
+            if self._text_tokens is not None:
+                self._text_pending = True
+        if getattr(self, "_text_pending", False):
+            # CLIP.encode_text on the device (fsar_text_encode), once per engine
+            if getattr(self._engine, "text_cfg", None) is None:
+                self._engine.text_configure(**self._text_geometry)
+                self._engine.load_clip_text_state_dict(self._text_state)
+            self.text_features_train = self._engine.text_encode(self._text_tokens[0]).cpu()
+            self.text_features_test = self._engine.text_encode(self._text_tokens[1]).cpu()
+            self._text_pending = False
             self._pushed_versions = None
         versions = tuple(p._version for p in self.parameters())
         if versions != self._pushed_versions:

@@ -23,7 +23,7 @@ SYMBOLS = [
     "fsar_missing_weights", "fsar_missing_weight", "fsar_vit_forward", "fsar_modulate", "fsar_otam_logits",
     "fsar_episode_forward", "fsar_episode_forward_host", "fsar_episode_submit_host", "fsar_episode_collect_host",
     "fsar_episodes_forward", "fsar_episodes_submit_host", "fsar_episodes_collect_host",
-    "fsar_preprocess_u8", "fsar_episodes_submit_host_u8", "fsar_metrics_update", "fsar_peek", "fsar_operand_dtype", "fsar_op_layernorm", "fsar_op_gemm", "fsar_op_attention", "fsar_op_f32_to_16",
+    "fsar_preprocess_u8", "fsar_episodes_submit_host_u8", "fsar_text_configure", "fsar_text_encode", "fsar_metrics_update", "fsar_peek", "fsar_operand_dtype", "fsar_op_layernorm", "fsar_op_gemm", "fsar_op_attention", "fsar_op_f32_to_16",
     "fsar_launch_count", "fsar_profile_begin", "fsar_profile_end",
 ]
 
@@ -51,6 +51,11 @@ class FsarEpisode(Structure):
         ("way", c_int32), ("merge_before", c_int32), ("single_direct", c_int32), ("text_mode", c_int32),
         ("text_coff", c_float),
     ]
+
+
+class FsarTextConfig(Structure):
+    _fields_ = [("width", c_int32), ("layers", c_int32), ("heads", c_int32), ("context_length", c_int32),
+                ("vocab_size", c_int32)]
 
 
 class FsarProfile(Structure):
@@ -101,6 +106,8 @@ def load_library(path=None):
     F3 = c_float * 3
     lib.fsar_preprocess_u8.argtypes = [H, c_void_p, c_int, c_int, c_int, c_int, c_int, F3, F3, c_void_p, c_void_p]
     lib.fsar_episodes_submit_host_u8.argtypes = [H, c_int, POINTER(FsarEpisode), c_int, c_int, c_int, c_int, c_int, F3, F3]
+    lib.fsar_text_configure.argtypes = [H, POINTER(FsarTextConfig)]
+    lib.fsar_text_encode.argtypes = [H, c_void_p, c_int, c_void_p, c_void_p]
     lib.fsar_metrics_update.argtypes = [H, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
     lib.fsar_peek.argtypes = [H, c_char_p, c_void_p, c_int64, c_void_p]
     lib.fsar_peek.restype = c_int64
@@ -391,6 +398,41 @@ class Engine:
             c_void_p(counters.data_ptr()), c_void_p(per_class.data_ptr()) if per_class is not None else None,
             self._stream()))
         return counters
+
+    # ------------------------------------------------------------------ CLIP text tower (init-time text features)
+    def text_configure(self, width, layers, heads, context_length=77, vocab_size=49408):
+        """Register the text tower's weights ('clip.*' = CLIP state_dict keys); then push them with set_weight /
+        load_state_dict(prefix) and call text_encode."""
+        tc = FsarTextConfig(width=int(width), layers=int(layers), heads=int(heads), context_length=int(context_length),
+                            vocab_size=int(vocab_size))
+        self._check(self.lib.fsar_text_configure(self._h, byref(tc)))
+        self.text_cfg = tc
+
+    def load_clip_text_state_dict(self, clip_state):
+        """Push the text-side tensors of an OpenAI CLIP state_dict (CLIP.encode_text, few_shot.py:793-806): everything
+        except 'visual.*', 'logit_scale' and the non-parameter entries of TorchScript archives."""
+        skip = ("visual.", "logit_scale", "input_resolution", "context_length", "vocab_size")
+        n = 0
+        for k, v in clip_state.items():
+            if k.startswith(skip):
+                continue
+            self.set_weight("clip." + k, v)
+            n += 1
+        return n
+
+    def text_encode(self, tokens):
+        """tokens: int [n, context_length] (tokenize(), few_shot.py:393-429) -> fp32 [n, embed_dim] on the device."""
+        torch = self._torch
+        t = tokens.to(device=self.device, dtype=torch.int32).contiguous()
+        tc = getattr(self, "text_cfg", None)
+        if tc is None:
+            raise FsarError(-5, "text_encode: call text_configure first")
+        if t.dim() != 2 or t.shape[1] != tc.context_length:
+            raise ValueError("tokens must be [n, %d], got %s" % (tc.context_length, tuple(t.shape)))
+        out = torch.empty(t.shape[0], self.cfg.embed_dim, device=self.device, dtype=torch.float32)
+        self._check(self.lib.fsar_text_encode(self._h, c_void_p(t.data_ptr()), t.shape[0], c_void_p(out.data_ptr()),
+                                              self._stream()))
+        return out
 
     def peek(self, name, shape, dtype=None):
         torch = self._torch

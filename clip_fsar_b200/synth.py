@@ -19,6 +19,63 @@ GEOMETRIES = {
 }
 
 
+# CLIP text towers paired with the visual geometries above (few_shot.py:849-886 build_model reads them off the
+# checkpoint: transformer_width, heads = width // 64, layers, context 77, vocab 49408).
+TEXT_GEOMETRIES = {
+    "ViT-B/16": dict(width=512, layers=12, heads=8, context_length=77, vocab_size=49408),
+    "ViT-L/14": dict(width=768, layers=12, heads=12, context_length=77, vocab_size=49408),
+    "tiny": dict(width=128, layers=2, heads=2, context_length=77, vocab_size=49408),
+    "small": dict(width=256, layers=3, heads=4, context_length=77, vocab_size=49408),
+}
+
+
+def text_state_dict_shapes(tg, embed_dim):
+    """CLIP state_dict keys of the text side (few_shot.py:735-744) -> shapes."""
+    W = tg["width"]
+    s = {"token_embedding.weight": (tg["vocab_size"], W), "positional_embedding": (tg["context_length"], W),
+         "ln_final.weight": (W,), "ln_final.bias": (W,), "text_projection": (W, embed_dim)}
+    for i in range(tg["layers"]):
+        p = "transformer.resblocks.%d." % i
+        s[p + "attn.in_proj_weight"] = (3 * W, W)
+        s[p + "attn.in_proj_bias"] = (3 * W,)
+        s[p + "attn.out_proj.weight"] = (W, W)
+        s[p + "attn.out_proj.bias"] = (W,)
+        for ln in ("ln_1", "ln_2"):
+            s[p + ln + ".weight"] = (W,)
+            s[p + ln + ".bias"] = (W,)
+        s[p + "mlp.c_fc.weight"] = (4 * W, W)
+        s[p + "mlp.c_fc.bias"] = (4 * W,)
+        s[p + "mlp.c_proj.weight"] = (W, 4 * W)
+        s[p + "mlp.c_proj.bias"] = (W,)
+    return s
+
+
+def synth_text_state_dict(tg, embed_dim, seed=3):
+    """Seeded text-tower weights with spread-out statistics (perturbed LayerNorm affine terms, sharper attention) so the
+    class embeddings differ visibly between prompts."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    W = tg["width"]
+    for name, shape in text_state_dict_shapes(tg, embed_dim).items():
+        if name == "token_embedding.weight":
+            v = 0.5 * rng.standard_normal(shape, dtype=np.float32)
+        elif name == "positional_embedding":
+            v = 0.2 * rng.standard_normal(shape)
+        elif name.endswith(".weight") and (".ln_" in name or name.startswith("ln_final")):
+            v = 1.0 + 0.25 * rng.standard_normal(shape)
+        elif name.endswith(".bias") and (".ln_" in name or name.startswith("ln_final")):
+            v = 0.15 * rng.standard_normal(shape)
+        elif name.endswith("bias"):
+            v = 0.1 * rng.standard_normal(shape)
+        elif name == "text_projection":
+            v = W ** -0.5 * rng.standard_normal(shape)
+        else:
+            gain = 2.0 if "in_proj_weight" in name else 1.0
+            v = gain * shape[1] ** -0.5 * rng.standard_normal(shape)
+        out[name] = np.ascontiguousarray(v, dtype=np.float32)
+    return out
+
+
 def full_geometry(name, mod_depth=1):
     g = dict(GEOMETRIES[name])
     g.update(mod_heads=8, mod_dim_head=g["embed_dim"] // 8, mod_mlp_dim=2048, mod_depth=mod_depth)

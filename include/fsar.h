@@ -163,6 +163,29 @@ int fsar_preprocess_u8(fsar_handle* h, const uint8_t* frames_u8_dev, int n_frame
 int fsar_episodes_submit_host_u8(fsar_handle* h, int slot, const fsar_episode* eps_host_u8, int n_episodes, int H, int W,
                                  int resize_h, int resize_w, const float mean[3], const float std[3]);
 
+/* CLIP text tower: CLIP.encode_text (few_shot.py:793-806) = token + positional embedding, `layers`
+ * ResidualAttentionBlocks (619-640) under the causal mask of build_attention_mask (777-783), ln_final on the
+ * end-of-text position (text.argmax(-1)), @ text_projection. It is what CNN_OTAM_CLIPFSAR.__init__ runs once to produce
+ * text_features_{train,test} (few_shot.py:2714-2728) from tokenize("a photo of {class}") (393-429; the BPE tokenizer
+ * stays on the host, this entry point takes token ids).
+ * fsar_text_configure registers the tower's weights under their CLIP state_dict names with a "clip." prefix:
+ *   clip.token_embedding.weight [vocab, width], clip.positional_embedding [context, width],
+ *   clip.transformer.resblocks.{i}.{attn.in_proj_weight, attn.in_proj_bias, attn.out_proj.{weight,bias},
+ *   ln_1.{weight,bias}, ln_2.{weight,bias}, mlp.c_fc.{weight,bias}, mlp.c_proj.{weight,bias}},
+ *   clip.ln_final.{weight,bias}, clip.text_projection [width, embed_dim]
+ * (set them with fsar_set_weight; they are not needed by the episode entry points). The blocks run on the frame
+ * encoder's kernels and workspace: width must be a multiple of 128 with heads * 64 == width, context_length <= 208. */
+typedef struct fsar_text_config {
+    int32_t width;           /* 512 (ViT-B/16, ViT-B/32), 768 (ViT-L/14) */
+    int32_t layers;          /* 12 */
+    int32_t heads;           /* width / 64 */
+    int32_t context_length;  /* 77 */
+    int32_t vocab_size;      /* 49408 */
+} fsar_text_config;
+int fsar_text_configure(fsar_handle* h, const fsar_text_config* cfg);
+/* tokens_dev int32 [n_texts, context_length] (tokenize(), few_shot.py:393-429) -> out_dev fp32 [n_texts, embed_dim]. */
+int fsar_text_encode(fsar_handle* h, const int32_t* tokens_dev, int n_texts, float* out_dev, void* stream);
+
 /* Caller-side metrics (runs/test_net_few_shot.py:111 cross-entropy, 147 topks_correct, 151-160 per-class accuracy) kept
  * on the device: counters_dev int64[3] += {n_correct_top1, n_queries, round(sum CE * 1e6)}; per_class_dev (may be NULL)
  * int64[2 * way] += {hits per class | queries per class}. No host synchronisation; read the counters once per run. */

@@ -65,7 +65,7 @@ def _rnd(x, dt):
     return x if dt is None else x.to(dt).float()
 
 
-def residual_block(x, sd, p, heads, dt=None):
+def residual_block(x, sd, p, heads, dt=None, mask=None):
     """ResidualAttentionBlock.forward, few_shot.py:633-640 with nn.MultiheadAttention(d, heads) (623, 635):
     no mask, no dropout in eval, head_dim ** -0.5 scaling of q. x: [n, L, D].
     dt != None additionally rounds every GEMM operand to that 16-bit type exactly where the CUDA path stores one
@@ -80,6 +80,8 @@ def residual_block(x, sd, p, heads, dt=None):
     k = k.reshape(n, L, heads, dh).transpose(1, 2)
     v = v.reshape(n, L, heads, dh).transpose(1, 2)
     s = (q @ k.transpose(-1, -2)) * dh ** -0.5
+    if mask is not None:   # additive attn_mask of the text transformer (few_shot.py:635, 777-783)
+        s = s + mask
     if dt is None:
         o = torch.softmax(s, dim=-1) @ v
     else:  # un-normalised numerators are the 16-bit P operand; the fp32 row sum divides afterwards
@@ -116,6 +118,21 @@ def vit_forward(sd, g, frames, taps=None, chunk=16, operand_dtype=None):
         x = layer_norm(x[:, 0, :], sd["backbone.ln_post.weight"], sd["backbone.ln_post.bias"])  # 683
         outs.append(x @ sd["backbone.proj"])                                                   # 686
     return torch.cat(outs, dim=0)
+
+
+def text_encode(sd, tg, tokens, operand_dtype=None):
+    """CLIP.encode_text, few_shot.py:793-806: token + positional embedding, the ResidualAttentionBlocks of
+    Transformer (643-651) under build_attention_mask (777-783: -inf above the diagonal), ln_final, the row of the
+    largest token id (end of text) @ text_projection. sd: CLIP state_dict keys of the text side. tokens: int [n, C]."""
+    sd = {k: _t(v) for k, v in sd.items()}
+    tokens = _t(tokens).long()
+    n, C = tokens.shape
+    x = sd["token_embedding.weight"][tokens] + sd["positional_embedding"]                   # 794-796
+    mask = torch.full((C, C), float("-inf")).triu_(1)                                        # 777-783
+    for i in range(tg["layers"]):                                                            # 797-799
+        x = residual_block(x, sd, "transformer.resblocks.%d." % i, tg["heads"], operand_dtype, mask=mask)
+    x = layer_norm(x, sd["ln_final.weight"], sd["ln_final.bias"])                            # 800
+    return x[torch.arange(n), tokens.argmax(dim=-1)] @ sd["text_projection"]                 # 804
 
 
 def modulator(sd, g, x):

@@ -194,6 +194,48 @@ def run_preproc_case(name, out_dir):
     print("%-28s out %s -> %s (%d KB)" % (name, out.shape, path, os.path.getsize(path) // 1024))
 
 
+TEXT_CASES = {
+    # name: text geometry (clip_fsar_b200/synth.py TEXT_GEOMETRIES), embed_dim, prompt template, class names
+    "text_tiny": dict(geom="tiny", embed_dim=128, prompt="a photo of {}",
+                      names=["riding a bike", "playing guitar", "jumping", "x", "pouring water into a glass of water slowly"]),
+    # the real ViT-B/16 text tower: width 512, 8 heads, 12 layers; SSv2-style and Kinetics-style class names
+    "text_vitb16": dict(geom="ViT-B/16", embed_dim=512, prompt="a photo of {}",
+                        names=["Pouring something into something", "Pushing something so that it falls off the table",
+                               "air drumming", "blasting sand", "busking", "cutting watermelon", "dancing ballet",
+                               "diving cliff", "filling eyebrows", "folding paper", "hula hooping", "ice skating",
+                               "paragliding", "playing trumpet", "shearing sheep", "unboxing"]),
+    "text_tiny_prompt": dict(geom="tiny", embed_dim=128, prompt="a video of a person {}, a type of action",
+                             names=["stretching arm", "throwing axe", "side kick"]),
+}
+
+
+def run_text_case(name, fs, out_dir):
+    """Token ids from the reference's own BPE tokenizer (few_shot.py:393-429, bpe_simple_vocab_16e6.txt.gz) and text
+    features from the reference's own CLIP.encode_text (793-806) with the seeded text-tower weights loaded into it."""
+    c = TEXT_CASES[name]
+    tg = synth.TEXT_GEOMETRIES[c["geom"]]
+    E = c["embed_dim"]
+    sd = synth.synth_text_state_dict(tg, E, seed=3)
+    clip = fs.CLIP(E, 32, 1, 128, 16, tg["context_length"], tg["vocab_size"], tg["width"], tg["heads"], tg["layers"]).float().eval()
+    res = clip.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    assert all(k.startswith("visual.") or k == "logit_scale" for k in res.missing_keys), res.missing_keys
+    prompts = [c["prompt"].format(nm) for nm in c["names"]]                       # few_shot.py:2715-2718
+    tokens = fs.tokenize(prompts)
+    with torch.no_grad():
+        feats = clip.encode_text(tokens)
+    meta = dict(case=name, geom=c["geom"], embed_dim=E, wseed=3, prompts=prompts, reference_commit="30cf0a8c",
+                torch=torch.__version__)
+    path = os.path.join(out_dir, name + ".npz")
+    np.savez_compressed(path, meta=np.array(json.dumps(meta)), tokens=tokens.numpy().astype(np.int32), features=feats.numpy(),
+                        weight_checksum=np.array([float(np.sum([np.float64(v).sum() for v in sd.values()]))]))
+    cs = torch.nn.functional.normalize(feats, dim=-1)
+    off = (cs @ cs.T - torch.eye(len(prompts))).abs().max().item()
+    print("%-26s features %s |f| %.3f max off-diagonal cosine %.3f eot %s -> %s (%d KB)" % (
+        name, tuple(feats.shape), feats.norm(dim=-1).mean().item(), off, tokens.argmax(-1).tolist()[:6], path,
+        os.path.getsize(path) // 1024))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -211,6 +253,10 @@ def main():
         if a.only and name != a.only:
             continue
         run_preproc_case(name, a.out)
+    for name in TEXT_CASES:
+        if a.only and name != a.only:
+            continue
+        run_text_case(name, fs, a.out)
 
 
 if __name__ == "__main__":

@@ -17,8 +17,8 @@ def pytest_configure(config):
 
 
 def golden_names():
-    """Episode fixtures (the preproc_* fixtures belong to tests/test_preprocess.py)."""
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("preproc_"))
+    """Episode fixtures (preproc_* belong to tests/test_preprocess.py, text_* to tests/test_text_tower.py)."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith(("preproc_", "text_")))
 
 
 def load_golden(name):

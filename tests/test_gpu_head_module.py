@@ -46,3 +46,42 @@ def test_module_forward_matches_reference_fixture(name, flags):
     assert torch.allclose(scaled["class_logits"], 2.0 * out["class_logits"], rtol=1e-5, atol=1e-7)
     loss = head.loss({"target_labels": dev["target_labels"]}, out)
     assert torch.isfinite(loss)
+
+
+def test_module_computes_text_features_with_the_text_tower():
+    """few_shot.py:2714-2728 through the drop-in module: class prompts -> (reference tokenizer's ids, from the fixture)
+    -> fsar_text_encode at the first forward. text_features_{train,test} must equal the reference's encode_text."""
+    from clip_fsar_b200 import synth
+    from clip_fsar_b200.head import CNN_OTAM_CLIPFSAR_SM100
+    tmeta, tref = load_golden("text_tiny")
+    names = [p[len("a photo of "):] for p in tmeta["prompts"]]
+    meta, ref = load_golden("tiny_5w1s")
+    g, sd, tt, te, task = regenerate(meta)
+    cfg = make_cfg(backbone="tiny", T=meta["T"])
+    cfg.TRAIN.CLASS_NAME, cfg.TEST.CLASS_NAME = names, names
+    seen = []
+
+    def tokenizer(prompts):
+        seen.append(list(prompts))
+        return torch.from_numpy(tref["tokens"])
+
+    head = CNN_OTAM_CLIPFSAR_SM100(cfg).cuda().eval()
+    tg = synth.TEXT_GEOMETRIES["tiny"]
+    head.set_clip_text({k: torch.from_numpy(v) for k, v in synth.synth_text_state_dict(tg, 128, tmeta["wseed"]).items()},
+                       tokenizer=tokenizer)
+    assert seen == [tmeta["prompts"], tmeta["prompts"]] and head._text_geometry == tg
+    head.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    dev = {k: torch.from_numpy(v).cuda() for k, v in task.items()}
+    dev["real_support_labels"] = dev["real_support_labels"] % len(names)
+    with torch.no_grad():
+        out = head(dev)
+    assert torch.isfinite(out["logits"]).all() and out["class_logits"].shape[1] == len(names)
+    for f in (head.text_features_train, head.text_features_test):
+        err = (f - torch.from_numpy(tref["features"])).abs().max() / abs(tref["features"]).max()
+        assert float(err) < 3e-3
+    # a second forward re-uses the features (no second encode): launch count of one episode only
+    n0 = head.engine().launch_count()
+    with torch.no_grad():
+        again = head(dev)
+    assert torch.equal(again["logits"], out["logits"])
+    assert head.engine().launch_count() - n0 < 60
