@@ -14,7 +14,9 @@
 //             tcgen05.st P into TMEM columns [0, LK/2) (aliasing the S columns already consumed)
 //   MMA     : O_g = P_g V    (A operand from TMEM, B = V tile as an MN-major smem operand, LK/16 k-steps,
 //             fp32 O in TMEM columns [128, 192) of group g, dead S columns by then)
-//   epilogue: tcgen05.ld O -> * 1/rowsum -> fp16 -> one 128-byte row per thread to global
+//   epilogue: tcgen05.ld O -> * 1/rowsum -> fp16 -> one 128-byte row per thread into a 128B-swizzled smem tile ->
+//             TMA store of the warp's 32 rows x 128 B through a [frame][token][D] tensor map (rows >= L are clipped, so
+//             a padded query tile never touches the next frame); full 128-byte lines instead of 16-byte fragments
 // Two row groups g (query rows 0-127 and 128-255) own TMEM columns [0,256) and [256,512) and 4 warps each, so the
 // tensor pipe works for one group while the other is in its softmax.
 // Warp roles (384 threads): 0 TMA producer, 1 / 3 MMA issuers of group 0 / 1, 2 TMEM allocator, 4-7 softmax group 0,
@@ -30,7 +32,8 @@ constexpr int ATT5_MAX_KEYS = 208;                       // 13 x 16; N of one tc
 constexpr int ATT5_Q_BYTES = 2 * 128 * 128;              // two 128-row query tiles, 128 B (64 x 16-bit) per row
 constexpr int ATT5_KV_BYTES = ATT5_MAX_KEYS * 128;       // 26 KB, multiple of 1024
 constexpr int ATT5_STAGE_BYTES = ATT5_Q_BYTES + 2 * ATT5_KV_BYTES;
-constexpr int ATT5_SMEM_BYTES = 2 * ATT5_STAGE_BYTES + 256 + 1024;
+constexpr int ATT5_OUT_TILE_BYTES = 32 * 128;             // output staging tile of one softmax warp: 32 rows x 128 B
+constexpr int ATT5_SMEM_BYTES = 2 * ATT5_STAGE_BYTES + 8 * ATT5_OUT_TILE_BYTES + 256 + 1024;
 constexpr uint32_t ATT5_O_COL = 128;                     // O accumulator columns inside a group's 256-column region
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -44,7 +47,7 @@ struct Att5Params {
     int LK;          // keys padded to a multiple of 16
     int n_mtiles;    // 1 or 2 query tiles of 128 rows
     float scale_log2e;
-    void* out;       // [n_frames * L, D] 16-bit
+    void* out;       // [n_frames * L, D] 16-bit (written through tmO)
     int reverse;     // walk the (frame, head) items last-to-first (L2 reuse of the QKV rows written last)
     int debug;       // only read by the -DFSAR_PROBES build (tools/gemm_probe.py, results WRONG): 1 skip the max pass,
                      // 2 no exp2, 4 no stores
@@ -55,11 +58,12 @@ struct Att5Params {
 template <typename T16, bool CAUSAL>
 __global__ void __launch_bounds__(ATT5_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                         const Att5Params p) {
+                         const __grid_constant__ CUtensorMap tmO, const Att5Params p) {
     constexpr bool kBf16 = std::is_same<T16, __nv_bfloat16>::value;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * ATT5_STAGE_BYTES);
+    uint8_t* smem_out = smem + 2 * ATT5_STAGE_BYTES;      // 8 softmax warps x [32 rows][128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + 8 * ATT5_OUT_TILE_BYTES);
     uint64_t* full_bar = bars;          // [2] TMA -> MMA
     uint64_t* empty_bar = bars + 2;     // [2] MMA -> TMA
     uint64_t* s_full = bars + 4;        // [2] per group: S ready
@@ -74,6 +78,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
         tma_prefetch_desc(&tmKV);
+        tma_prefetch_desc(&tmO);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -166,12 +171,13 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         if (g < p.n_mtiles) {
             const int row = g * 128 + wq * 32 + lane;     // query token of this thread
             const bool warp_valid = (g * 128 + wq * 32) < p.L;
-            const bool valid = row < p.L;
             const int n_keys = (CAUSAL && row + 1 < p.L) ? row + 1 : p.L;   // keys this query row may attend to
             const uint32_t t_row = tmem_base + g * 256 + (uint32_t(wq * 32) << 16);
             const int n32 = p.LK / 32;             // full 32-column chunks of the score row
             const bool tail16 = (p.LK & 16) != 0;  // plus one 16-column chunk
-            T16* out = reinterpret_cast<T16*>(p.out);
+            uint8_t* out_tile = smem_out + (warp - 4) * ATT5_OUT_TILE_BYTES;
+            const uint32_t out_row = smem_u32(out_tile) + lane * 128;
+            const uint32_t sw = uint32_t(lane & 7);     // 128B swizzle: 16-byte chunk index ^= row % 8
             int i = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
                 const uint32_t ip = i & 1;
@@ -277,29 +283,33 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&o_empty[g]);
-                if (valid && !FSAR_PROBE(p.debug, 4)) {
-                    const float inv = 1.0f / sum;
-                    uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)frame * p.L + row) * p.D + head * 64);
+                if (warp_valid && !FSAR_PROBE(p.debug, 4)) {
+                    const float inv = 1.0f / sum;      // rows >= L: garbage, clipped by the TMA store
+                    if (lane == 0) tma_store_wait_read<0>();   // the previous item's store has drained the tile
+                    __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 v;
-                        v.x = pack2<T16>(__uint_as_float(o0[8 * j]) * inv, __uint_as_float(o0[8 * j + 1]) * inv);
-                        v.y = pack2<T16>(__uint_as_float(o0[8 * j + 2]) * inv, __uint_as_float(o0[8 * j + 3]) * inv);
-                        v.z = pack2<T16>(__uint_as_float(o0[8 * j + 4]) * inv, __uint_as_float(o0[8 * j + 5]) * inv);
-                        v.w = pack2<T16>(__uint_as_float(o0[8 * j + 6]) * inv, __uint_as_float(o0[8 * j + 7]) * inv);
-                        dst[j] = v;
-                    }
+                    for (int j = 0; j < 4; ++j)
+                        st_shared_v4(out_row + ((uint32_t(j) ^ sw) << 4),
+                                     pack2<T16>(__uint_as_float(o0[8 * j]) * inv, __uint_as_float(o0[8 * j + 1]) * inv),
+                                     pack2<T16>(__uint_as_float(o0[8 * j + 2]) * inv, __uint_as_float(o0[8 * j + 3]) * inv),
+                                     pack2<T16>(__uint_as_float(o0[8 * j + 4]) * inv, __uint_as_float(o0[8 * j + 5]) * inv),
+                                     pack2<T16>(__uint_as_float(o0[8 * j + 6]) * inv, __uint_as_float(o0[8 * j + 7]) * inv));
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 v;
-                        v.x = pack2<T16>(__uint_as_float(o1[8 * j]) * inv, __uint_as_float(o1[8 * j + 1]) * inv);
-                        v.y = pack2<T16>(__uint_as_float(o1[8 * j + 2]) * inv, __uint_as_float(o1[8 * j + 3]) * inv);
-                        v.z = pack2<T16>(__uint_as_float(o1[8 * j + 4]) * inv, __uint_as_float(o1[8 * j + 5]) * inv);
-                        v.w = pack2<T16>(__uint_as_float(o1[8 * j + 6]) * inv, __uint_as_float(o1[8 * j + 7]) * inv);
-                        dst[4 + j] = v;
+                    for (int j = 0; j < 4; ++j)
+                        st_shared_v4(out_row + ((uint32_t(4 + j) ^ sw) << 4),
+                                     pack2<T16>(__uint_as_float(o1[8 * j]) * inv, __uint_as_float(o1[8 * j + 1]) * inv),
+                                     pack2<T16>(__uint_as_float(o1[8 * j + 2]) * inv, __uint_as_float(o1[8 * j + 3]) * inv),
+                                     pack2<T16>(__uint_as_float(o1[8 * j + 4]) * inv, __uint_as_float(o1[8 * j + 5]) * inv),
+                                     pack2<T16>(__uint_as_float(o1[8 * j + 6]) * inv, __uint_as_float(o1[8 * j + 7]) * inv));
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_3d(&tmO, out_tile, head * 64, g * 128 + wq * 32, frame);
+                        tma_store_commit();
                     }
                 }
             }
+            if (lane == 0) tma_store_wait<0>();   // every output tile is globally written before the CTA retires
         }
     }
 

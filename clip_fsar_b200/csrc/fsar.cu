@@ -235,6 +235,30 @@ int get_tmap(fsar_handle* h, const void* ptr, int rows, int cols, int box_rows, 
     return 0;
 }
 
+// [n_frames][L][D] view of a 16-bit [n_frames * L, D] matrix, box = [1][32 tokens][64 columns], 128-byte swizzle:
+// the attention core stores 32-row tiles through it and tokens >= L of a frame are clipped.
+int get_tmap_tokens3d(fsar_handle* h, const void* ptr, int n_frames, int L, int D, CUtensorMap* out) {
+    auto key = std::make_tuple(ptr, n_frames * 4096 + L, D, -3);
+    auto it = h->tmaps.find(key);
+    if (it != h->tmaps.end()) {
+        *out = it->second;
+        return 0;
+    }
+    CUtensorMap m;
+    cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)L, (cuuint64_t)n_frames};
+    cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)L * D * 2};
+    cuuint32_t box[3] = {64, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = h->encode(&m, kOperandDtype ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                           const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, FSAR_E_CUDA, "cuTensorMapEncodeTiled (3D) failed with %d (%d x %d x %d)", (int)r, n_frames, L, D);
+    if (h->tmaps.size() > 4096) h->tmaps.clear();
+    h->tmaps[key] = m;
+    *out = m;
+    return 0;
+}
+
 // ---------------------------------------------------------------- GEMM dispatch
 template <int BN, int EPI>
 int launch_gemm_inst(fsar_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
@@ -374,15 +398,16 @@ int attention(fsar_handle* h, const T16* qkv, int n_frames, int L, int heads, T1
         ap.n_frames = n_frames; ap.L = L; ap.heads = heads; ap.D = D;
         ap.LK = round_up(L, 16); ap.n_mtiles = (L + 127) / 128; ap.scale_log2e = scale_log2e; ap.out = out; ap.reverse = reverse;
         { const char* e = getenv("FSAR_ATT_DEBUG"); ap.debug = e ? atoi(e) : 0; }
-        CUtensorMap tq, tkv;
+        CUtensorMap tq, tkv, to;
         RET_IF(get_tmap(h, qkv, n_frames * L, 3 * D, 128, 64, 0, &tq));
         RET_IF(get_tmap(h, qkv, n_frames * L, 3 * D, ap.LK, 64, 0, &tkv));
+        RET_IF(get_tmap_tokens3d(h, out, n_frames, L, D, &to));
         const int items = n_frames * heads;
         const int grid5 = items < h->sms ? items : h->sms;
         if (causal)
-            launch_pdl(h, attention_tcgen05_kernel<T16, true>, dim3(grid5), dim3(ATT5_THREADS), ATT5_SMEM_BYTES, st, tq, tkv, ap);
+            launch_pdl(h, attention_tcgen05_kernel<T16, true>, dim3(grid5), dim3(ATT5_THREADS), ATT5_SMEM_BYTES, st, tq, tkv, to, ap);
         else
-            launch_pdl(h, attention_tcgen05_kernel<T16, false>, dim3(grid5), dim3(ATT5_THREADS), ATT5_SMEM_BYTES, st, tq, tkv, ap);
+            launch_pdl(h, attention_tcgen05_kernel<T16, false>, dim3(grid5), dim3(ATT5_THREADS), ATT5_SMEM_BYTES, st, tq, tkv, to, ap);
         return check_launch(h, "attention_tcgen05_kernel");
     }
     const dim3 grid((L + ATT_QROWS - 1) / ATT_QROWS, heads, n_frames);
