@@ -309,7 +309,11 @@ def main():
                "sample": "%d timed samples of 16 of the episode's 80 frames through the fp32 CPU ViT (extrapolated "
                          "linearly) + the full head, torch CPU ops on %d threads" % (n, cores)}
 
-    flops_ep = 80 * synth.vit_flops_per_frame(g)
+    # FLOPs: `flops_ref` is the reference-equivalent count (every token row of every block); the library
+    # EXECUTES fewer in the last block, where only the CLS row is read downstream. Rates are quoted on
+    # executed FLOPs (summed over the launches actually made), never on the skipped ones.
+    flops_ref = 80 * synth.vit_flops_per_frame(g)
+    flops_ep = sum(prof[k]["flops"] for k in prof if k.startswith("gemm_") or k in ("attention", "final_proj")) / NP
     line = {"metric": METRIC, "value": value, "unit": "episodes/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp16 operands / fp32 accumulate (reference: f32)", "data": "synthetic",
@@ -323,6 +327,9 @@ def main():
             "gpu_launches": launches * world, "clocks": clocks,
             "vit_tflops": flops_ep * args.steps * world / (ms_total / 1e3) / 1e12,
             "vit_frac_of_sustained_peak": flops_ep * args.steps / (ms_total / 1e3) / 1e12 / pk["tf_sustained"],
+            "vit_flops_per_episode": {"executed": flops_ep, "reference_equivalent": flops_ref,
+                                      "note": "last block: Q / out_proj / ln_2 / MLP on the CLS row only (the only row "
+                                              "ln_post reads); rates use executed FLOPs"},
             "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
     print(json.dumps(line), flush=True)
     if world > 1:

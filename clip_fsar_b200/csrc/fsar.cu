@@ -97,6 +97,7 @@ struct fsar_handle {
     std::vector<float*> mod_qkv;
     // ---- ViT workspace (capacity cfg.max_frames)
     T16 *patches16 = nullptr, *ln16 = nullptr, *qkv16 = nullptr, *att16 = nullptr, *h16 = nullptr;
+    T16 *cls_q16 = nullptr, *cls_att16 = nullptr, *cls_ln16 = nullptr, *cls_h16 = nullptr;   // last block: CLS rows only
     float* x32 = nullptr;
     // ---- head workspace
     float *feats = nullptr;  // [max_videos * max_tokens, E] support rows then target rows
@@ -113,7 +114,7 @@ struct fsar_handle {
                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     EncodeFn encode = nullptr;
-    std::map<std::tuple<const void*, int, int, int>, CUtensorMap> tmaps;
+    std::map<std::tuple<const void*, int, int, int, long long>, CUtensorMap> tmaps;
     // ---- host-buffer path
     HostSlot slot[2];
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
@@ -124,6 +125,7 @@ struct fsar_handle {
     bool alternate_rows = true;     // FSAR_NO_ALTERNATE=1: every kernel walks rows first-to-last (A/B testing)
     bool single_cta_gemm = false;   // FSAR_GEMM_SINGLE=1: one CTA per 128 x 256 tile instead of CTA pairs (A/B testing)
     int gemm_debug = 0;             // FSAR_GEMM_DEBUG: bottleneck probes, -DFSAR_PROBES build only (tools/gemm_probe.py)
+    bool cls_last_block = true;     // FSAR_FULL_LAST_BLOCK=1: the last block also computes the token rows nobody reads
     bool pdl = true;                // FSAR_NO_PDL=1: no programmatic dependent launch between the frame-encoder kernels
     bool legacy_attention = false;  // FSAR_LEGACY_ATTENTION=1: mma.sync attention core also for L <= 208 (A/B testing)
     std::vector<ProfRec> prof;
@@ -209,18 +211,22 @@ void launch_pdl(fsar_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, s
 // ---------------------------------------------------------------- TMA tensor maps
 // Row-major matrix [rows, cols] (cols contiguous) of 16-bit operands (f32 == 0) or fp32 (f32 == 1),
 // box = [box_rows, box_cols] with box_cols * elem_size == 128 bytes, 128-byte swizzle.
-int get_tmap(fsar_handle* h, const void* ptr, int rows, int cols, int box_rows, int box_cols, int f32, CUtensorMap* out) {
-    auto key = std::make_tuple(ptr, rows, cols, box_rows * 4 + f32 * 2 + (box_cols == 64 ? 1 : 0));
+// `pitch` = distance between rows in elements (0: cols): a pitch of tokens * width over the token matrix selects one row
+// per frame, e.g. the CLS rows.
+int get_tmap(fsar_handle* h, const void* ptr, int rows, int cols, int box_rows, int box_cols, int f32, CUtensorMap* out,
+             long long pitch = 0) {
+    if (pitch == 0) pitch = cols;
+    auto key = std::make_tuple(ptr, rows, cols, box_rows * 4 + f32 * 2 + (box_cols == 64 ? 1 : 0), pitch);
     auto it = h->tmaps.find(key);
     if (it != h->tmaps.end()) {
         *out = it->second;
         return 0;
     }
     const int esz = f32 ? 4 : 2;
-    if ((cols * esz) % 16 != 0) return fail(h, FSAR_E_INVALID, "TMA needs a 16-byte row pitch, got %d x %d bytes", cols, esz);
+    if ((pitch * esz) % 16 != 0) return fail(h, FSAR_E_INVALID, "TMA needs a 16-byte row pitch, got %lld x %d bytes", pitch, esz);
     CUtensorMap m;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)cols * esz};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * esz};
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
@@ -238,7 +244,7 @@ int get_tmap(fsar_handle* h, const void* ptr, int rows, int cols, int box_rows, 
 // [n_frames][L][D] view of a 16-bit [n_frames * L, D] matrix, box = [1][32 tokens][64 columns], 128-byte swizzle:
 // the attention core stores 32-row tiles through it and tokens >= L of a frame are clipped.
 int get_tmap_tokens3d(fsar_handle* h, const void* ptr, int n_frames, int L, int D, CUtensorMap* out) {
-    auto key = std::make_tuple(ptr, n_frames * 4096 + L, D, -3);
+    auto key = std::make_tuple(ptr, n_frames * 4096 + L, D, -3, 0LL);
     auto it = h->tmaps.find(key);
     if (it != h->tmaps.end()) {
         *out = it->second;
@@ -315,9 +321,9 @@ int launch_gemm_bn(fsar_handle* h, int epi, const CUtensorMap& ta, const CUtenso
     return fail(h, FSAR_E_INVALID, "unknown GEMM epilogue %d", epi);
 }
 
-// out[M,N] (epilogue) = A16[M,K] W16[N,K]^T (+ bias); K = row pitch of both operands, N = row pitch of out.
+// out[M,N] (epilogue) = A16[M,K] W16[N,K]^T (+ bias); W rows are K apart; A rows lda apart (0: K), out rows ldc (0: N).
 int gemm(fsar_handle* h, int cls, const T16* a, const T16* w, const float* bias, void* out, int M, int N, int K, int epi,
-         cudaStream_t st, int reverse = 0) {
+         cudaStream_t st, int reverse = 0, long long lda = 0, long long ldc = 0) {
     if (M <= 0 || N <= 0 || K <= 0 || (N % 8) != 0 || (K % 8) != 0)
         return fail(h, FSAR_E_INVALID, "gemm: unsupported shape M=%d N=%d K=%d (need N %% 8 == 0, K %% 8 == 0)", M, N, K);
     if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out)) & 15)
@@ -328,9 +334,9 @@ int gemm(fsar_handle* h, int cls, const T16* a, const T16* w, const float* bias,
     const bool out16 = (epi == EPI_STORE16 || epi == EPI_QGELU16);
     CUtensorMap ta, tb, tc;
     const bool pair = (bn == 256) && !h->single_cta_gemm;   // CTA pairs (cta_group::2, 256 x 256 tiles)
-    RET_IF(get_tmap(h, a, M, K, GEMM_BM, GEMM_BK, 0, &ta));
+    RET_IF(get_tmap(h, a, M, K, GEMM_BM, GEMM_BK, 0, &ta, lda));
     RET_IF(get_tmap(h, w, N, K, pair ? GEMM2_BN / 2 : bn, GEMM_BK, 0, &tb));
-    RET_IF(get_tmap(h, out, M, N, 32, out16 ? 64 : 32, out16 ? 0 : 1, &tc));
+    RET_IF(get_tmap(h, out, M, N, 32, out16 ? 64 : 32, out16 ? 0 : 1, &tc, ldc));
     Scope s(h, st, cls, 2.0 * M * N * K, 0.0);
     if (pair) return launch_gemm_pair(h, epi, ta, tb, tc, p, st);
     if (bn == 256) return launch_gemm_bn<256>(h, epi, ta, tb, tc, p, st);
@@ -360,19 +366,22 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, T16* __restric
     dst[i] = (c < cols) ? T16(src[(size_t)r * cols + c]) : T16(0.f);
 }
 
+// in_pitch: distance between input rows in elements (0: D); the output is always dense.
 int layernorm(fsar_handle* h, const float* x, void* out, const float* g, const float* b, int rows, int D, bool out16,
-              bool embed, int tokens, const float* cls_emb, const float* pos, cudaStream_t st, int cls, int reverse = 0) {
+              bool embed, int tokens, const float* cls_emb, const float* pos, cudaStream_t st, int cls, int reverse = 0,
+              long long in_pitch = 0) {
+    if (in_pitch == 0) in_pitch = D;
     if ((D % 128) != 0 || D > 1024) return fail(h, FSAR_E_INVALID, "layernorm: dim %d must be a multiple of 128 and <= 1024", D);
     const int wpb = 8;
     const int grid = (rows + wpb - 1) / wpb;
     Scope s(h, st, cls, 0.0, (double)rows * D * (4.0 + (out16 ? 2.0 : 4.0)));
     const float* np = nullptr;
     if (embed)
-        launch_pdl(h, layernorm_kernel<T16, false, true>, dim3(grid), dim3(256), 0, st, x, out, g, b, rows, D, 1e-5f, tokens, cls_emb, pos, reverse);
+        launch_pdl(h, layernorm_kernel<T16, false, true>, dim3(grid), dim3(256), 0, st, x, out, g, b, rows, D, 1e-5f, tokens, cls_emb, pos, reverse, in_pitch);
     else if (out16)
-        launch_pdl(h, layernorm_kernel<T16, true, false>, dim3(grid), dim3(256), 0, st, x, out, g, b, rows, D, 1e-5f, tokens, np, np, reverse);
+        launch_pdl(h, layernorm_kernel<T16, true, false>, dim3(grid), dim3(256), 0, st, x, out, g, b, rows, D, 1e-5f, tokens, np, np, reverse, in_pitch);
     else
-        launch_pdl(h, layernorm_kernel<T16, false, false>, dim3(grid), dim3(256), 0, st, x, out, g, b, rows, D, 1e-5f, tokens, np, np, reverse);
+        launch_pdl(h, layernorm_kernel<T16, false, false>, dim3(grid), dim3(256), 0, st, x, out, g, b, rows, D, 1e-5f, tokens, np, np, reverse, in_pitch);
     return check_launch(h, "layernorm_kernel");
 }
 
@@ -553,6 +562,10 @@ int alloc_workspace(fsar_handle* h) {
     RET_IF(dalloc(h, &h->qkv16, M * 3 * D));
     RET_IF(dalloc(h, &h->att16, M * D));
     RET_IF(dalloc(h, &h->h16, M * 4 * D));
+    RET_IF(dalloc(h, &h->cls_q16, (size_t)c.max_frames * D));
+    RET_IF(dalloc(h, &h->cls_att16, (size_t)c.max_frames * D));
+    RET_IF(dalloc(h, &h->cls_ln16, (size_t)c.max_frames * D));
+    RET_IF(dalloc(h, &h->cls_h16, (size_t)c.max_frames * 4 * D));
     const size_t V = c.max_videos, T = c.max_tokens;
     const size_t rows = V * (T + 1);
     const size_t inner = (size_t)c.mod_heads * c.mod_dim_head;
@@ -635,6 +648,33 @@ int vit_encode_gathered(fsar_handle* h, int n, float* feats_out, cudaStream_t st
         RET_IF(layernorm(h, h->x32, h->ln16, W32(h, pre + "ln_1.weight"), W32(h, pre + "ln_1.bias"), M, D, true, false, L,
                          nullptr, nullptr, st, FSAR_K_LAYERNORM, dir));
         dir ^= flip;
+        if (i == c.layers - 1 && h->cls_last_block && L <= CLS_ATT_MAX_L) {
+            // Last block: only x[:, 0, :] survives the transformer (ln_post(x[:, 0, :]) @ proj, few_shot.py:683-686), so
+            // all tokens feed K and V, but Q, the attention output, out_proj, ln_2 and the MLP are evaluated for the
+            // CLS row of every frame only -- the same numbers the full block would leave in those rows. Row pitches of
+            // L * D address the CLS rows of ln16 / x32 in place.
+            const long long cls_pitch = (long long)L * D;
+            const T16* w_in = W16(h, pre + "attn.in_proj_weight");
+            const float* b_in = W32(h, pre + "attn.in_proj_bias");
+            T16* kv16 = h->qkv16;   // [M, 2 D]
+            RET_IF(gemm(h, FSAR_K_GEMM_QKV, h->ln16, w_in + (size_t)D * D, b_in + D, kv16, M, 2 * D, D, EPI_STORE16, st, dir));
+            RET_IF(gemm(h, FSAR_K_GEMM_QKV, h->ln16, w_in, b_in, h->cls_q16, n, D, D, EPI_STORE16, st, 0, cls_pitch));
+            {
+                Scope s(h, st, FSAR_K_ATTENTION, 4.0 * n * c.heads * (double)L * ATT_HD, (double)M * 2 * D * 2.0);
+                launch_pdl(h, cls_attention_kernel<T16>, dim3(c.heads, n), dim3(128), 0, st, (const T16*)h->cls_q16,
+                           (const T16*)kv16, h->cls_att16, L, D, 0.125f * 1.4426950408889634f);
+                RET_IF(check_launch(h, "cls_attention_kernel"));
+            }
+            RET_IF(gemm(h, FSAR_K_GEMM_OUT, h->cls_att16, W16(h, pre + "attn.out_proj.weight"),
+                        W32(h, pre + "attn.out_proj.bias"), h->x32, n, D, D, EPI_RESID32, st, 0, 0, cls_pitch));
+            RET_IF(layernorm(h, h->x32, h->cls_ln16, W32(h, pre + "ln_2.weight"), W32(h, pre + "ln_2.bias"), n, D, true, false,
+                             L, nullptr, nullptr, st, FSAR_K_LAYERNORM, 0, cls_pitch));
+            RET_IF(gemm(h, FSAR_K_GEMM_FC1, h->cls_ln16, W16(h, pre + "mlp.c_fc.weight"), W32(h, pre + "mlp.c_fc.bias"),
+                        h->cls_h16, n, 4 * D, D, EPI_QGELU16, st));
+            RET_IF(gemm(h, FSAR_K_GEMM_FC2, h->cls_h16, W16(h, pre + "mlp.c_proj.weight"), W32(h, pre + "mlp.c_proj.bias"),
+                        h->x32, n, D, 4 * D, EPI_RESID32, st, 0, 0, cls_pitch));
+            break;
+        }
         RET_IF(gemm(h, FSAR_K_GEMM_QKV, h->ln16, W16(h, pre + "attn.in_proj_weight"), W32(h, pre + "attn.in_proj_bias"),
                     h->qkv16, M, 3 * D, D, EPI_STORE16, st, dir));
         dir ^= flip;
@@ -947,6 +987,8 @@ int fsar_create(const fsar_config* cfg, fsar_handle** out) {
         h->single_cta_gemm = (e != nullptr && e[0] == '1');
         e = getenv("FSAR_GEMM_DEBUG");
         h->gemm_debug = e != nullptr ? atoi(e) : 0;
+        e = getenv("FSAR_FULL_LAST_BLOCK");
+        h->cls_last_block = !(e != nullptr && e[0] == '1');
         e = getenv("FSAR_NO_PDL");
         h->pdl = !(e != nullptr && e[0] == '1');
     }
@@ -997,7 +1039,8 @@ void fsar_destroy(fsar_handle* h) {
         if (w.d16) cudaFree(w.d16);
     }
     for (float* p : h->mod_qkv) if (p) cudaFree(p);
-    void* bufs[] = {h->patches16, h->ln16, h->qkv16, h->att16, h->h16, h->x32, h->feats};
+    void* bufs[] = {h->patches16, h->ln16, h->qkv16, h->att16, h->h16, h->x32, h->feats,
+                    h->cls_q16, h->cls_att16, h->cls_ln16, h->cls_h16};
     for (void* p : bufs) if (p) cudaFree(p);
     for (HeadWs& w : h->ws) {
         void* wb[] = {w.seq, w.mod_ln, w.mod_qkvbuf, w.mod_att, w.mod_y, w.mod_h, w.mod_out, w.mod_tmp, w.protos, w.dists, w.cum,

@@ -97,6 +97,7 @@ __global__ void patch_gather_kernel(const float* __restrict__ frames, T16* __res
 // ------------------------------------------------------------------------------------------------
 // LayerNorm over the last dimension, one warp per row, statistics in fp32 (two-pass in registers).
 //   D % 128 == 0, D <= 1024.  OUT16: write T16, else write fp32 (may alias the input: in-place).
+//   Input rows are in_pitch elements apart (in_pitch = tokens * D picks the CLS row of every frame), output rows D.
 //   EMBED (ln_pre, few_shot.py:675-677): the input row of (frame f, token t) is assembled on the fly as
 //     t == 0 : class_embedding + positional_embedding[0]
 //     t >= 1 : patch_out[f * (tokens - 1) + t - 1] + positional_embedding[t]     (patch_out = conv1 GEMM output)
@@ -105,7 +106,7 @@ template <typename T16, bool OUT16, bool EMBED>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x, void* out, const float* __restrict__ gamma, const float* __restrict__ beta,
                  int rows, int D, float eps, int tokens, const float* __restrict__ cls_emb,
-                 const float* __restrict__ pos, int reverse) {
+                 const float* __restrict__ pos, int reverse, long long in_pitch) {
     pdl_trigger();
     pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -114,7 +115,7 @@ layernorm_kernel(const float* x, void* out, const float* __restrict__ gamma, con
     if (reverse) row = rows - 1 - row;   // blocks are scheduled in index order: last rows first
     const int nv = D >> 7;  // float4 per lane
     float4 v[8];
-    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * in_pitch);
     const float4* pr = nullptr;
     bool is_cls = false;
     if (EMBED) {
@@ -259,6 +260,72 @@ final_proj_kernel(const float* __restrict__ x, const float* __restrict__ gamma, 
             if (f0 + f < n_frames) out[(size_t)(f0 + f) * E + e] = v;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Attention of the CLS query only, for the LAST block of the frame encoder: VisionTransformer.forward keeps only
+// x[:, 0, :] after the transformer (few_shot.py:683), so in the last ResidualAttentionBlock every token still feeds K
+// and V but only the CLS row of Q, of the attention output and of the MLP is ever used.
+//   q16  [n_frames, D]            (CLS rows of Q, bias included)
+//   kv16 [n_frames * L, 2 D]      (K | V column blocks, head h at h * 64)
+//   out16 [n_frames, D]
+// One CTA per (head, frame), 128 threads. Numerics mirror the tensor-core path: fp32 scores and row sum, un-normalised
+// probabilities rounded to the 16-bit operand type before P V, fp32 accumulation, one division at the end.
+constexpr int CLS_ATT_MAX_L = 272;
+template <typename T16>
+__global__ void __launch_bounds__(128)
+cls_attention_kernel(const T16* __restrict__ q16, const T16* __restrict__ kv16, T16* __restrict__ out16, int L, int D,
+                     float scale_log2e) {
+    __shared__ float qs[64];
+    __shared__ float sc[CLS_ATT_MAX_L];
+    __shared__ float red[4];
+    __shared__ float part[64];
+    pdl_trigger();
+    pdl_wait();
+    const int head = blockIdx.x, frame = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < 64) qs[tid] = float(q16[(size_t)frame * D + head * 64 + tid]);
+    __syncthreads();
+    const T16* kbase = kv16 + (size_t)frame * L * 2 * D + head * 64;
+    float mx = -INFINITY;
+    for (int j = tid; j < L; j += 128) {
+        const uint4* kr = reinterpret_cast<const uint4*>(kbase + (size_t)j * 2 * D);
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint4 v = __ldg(kr + c);
+            const T16* e = reinterpret_cast<const T16*>(&v);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) s = fmaf(qs[c * 8 + t], float(e[t]), s);
+        }
+        sc[j] = s;
+        mx = fmaxf(mx, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])) * scale_log2e;
+    __syncthreads();
+    float sum = 0.f;
+    for (int j = tid; j < L; j += 128) {
+        const float e = exp2f(fmaf(sc[j], scale_log2e, -mx));
+        sum += e;
+        sc[j] = float(T16(e));          // the P operand is 16-bit in the tensor-core path
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    sum = (red[0] + red[1]) + (red[2] + red[3]);
+    // O[d] = sum_j p_j V[j][d]: threads 0-63 take the even keys, 64-127 the odd keys of column d = tid % 64
+    const int d = tid & 63, par = tid >> 6;
+    const T16* vbase = kbase + D + d;
+    float acc = 0.f;
+    for (int j = par; j < L; j += 2) acc = fmaf(sc[j], float(vbase[(size_t)j * 2 * D]), acc);
+    if (par == 1) part[d] = acc;
+    __syncthreads();
+    if (par == 0) out16[(size_t)frame * D + head * 64 + d] = T16((acc + part[d]) / sum);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -307,3 +307,26 @@ def test_full_size_matches_fixture_and_counts_launches(full):
     logits, _ = run(e, meta, task)
     assert e.launch_count() - n0 > 50                                           # our kernels ran, not a fallback
     assert rel_max(logits, ref["logits"]) < 3e-3
+
+
+@pytest.mark.parametrize("name", ["tiny_5w1s", "small_5w1s"])
+def test_cls_only_last_block_equals_full_last_block(lib, name, monkeypatch):
+    """The last transformer block evaluates Q / out_proj / ln_2 / MLP for the CLS row only (the only row
+    VisionTransformer.forward keeps, few_shot.py:683). FSAR_FULL_LAST_BLOCK=1 computes every token row as the reference
+    does: the frame features must agree to operand-rounding noise (the CLS attention row is SIMT fp32 instead of
+    tcgen05, everything else is the same kernels on the same rows)."""
+    meta, ref = load_golden(name)
+    g, sd, tt, te, task = regenerate(meta)
+    frames = torch.from_numpy(task["support_set"]).to(DEV)
+    feats = {}
+    for full_block in ("0", "1"):
+        monkeypatch.setenv("FSAR_FULL_LAST_BLOCK", full_block)
+        e = make_engine(lib, meta, g, sd, tt, te)
+        n0 = e.launch_count()
+        feats[full_block] = e.vit_forward(frames).cpu()
+        launches = e.launch_count() - n0
+        e.close()
+        # patch gather + patch GEMM + ln_pre + 7 per block + final projection; the CLS-only block has 8 launches
+        assert launches == 4 + 7 * g["layers"] + (1 if full_block == "0" else 0)
+    assert rel_max(feats["0"], feats["1"]) < 5e-4
+    assert rel_l2(feats["0"], ref["support_feats"].reshape(-1, g["embed_dim"])) < 5e-3
