@@ -158,6 +158,8 @@ def main():
     ap.add_argument("--batch", type=int, default=6,
                     help="episodes per fsar_episodes_* call; their 80-frame sets are regrouped into 96-frame ViT passes "
                          "(whole waves of 256x256 tiles on 148 SMs). 1 = one episode per call")
+    ap.add_argument("--pass-frames", type=int, default=96,
+                    help="frames per ViT pass when --batch > 1 (96 x 197 rows = 74 row blocks of 256 = one per CTA pair)")
     ap.add_argument("--pool", type=int, default=6, help="distinct resident episodes cycled (6 x 48 MB > 126 MB L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -183,7 +185,7 @@ def main():
 
     g = synth.full_geometry(GEOM)
     n_vid = WAY * (SHOT + QPC)
-    frames_per_pass = 96 if B > 1 else n_vid * T
+    frames_per_pass = args.pass_frames if B > 1 else n_vid * T
     eng = L.Engine(**dict(g, max_frames=frames_per_pass, max_videos=n_vid, max_tokens=T, max_classes=max(N_TRAIN, N_TEST),
                           max_batch=B, otam_lambda=0.5, device=local))
     sd_np = synth.synth_state_dict(g, 0, spread=False)

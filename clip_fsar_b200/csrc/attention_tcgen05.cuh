@@ -1,4 +1,5 @@
-// Attention core of the CLIP ViT on the 5th-generation tensor cores (tcgen05 + TMEM), for L <= 208 tokens.
+// Attention core of the CLIP ViT on the 5th-generation tensor cores (tcgen05 + TMEM), for L <= 257 tokens
+// (197 = ViT-B/16, 257 = ViT-L/14 at 224 x 224, 77 = the causal text transformer).
 //
 //   out[f, :, h] = softmax(Q K^T / sqrt(64)) V      per (frame f, head h); no mask, no dropout
 //   (nn.MultiheadAttention in eval mode, /root/reference/models/base/few_shot.py:623, 635)
@@ -21,6 +22,15 @@
 // tensor pipe works for one group while the other is in its softmax.
 // Warp roles (384 threads): 0 TMA producer, 1 / 3 MMA issuers of group 0 / 1, 2 TMEM allocator, 4-7 softmax group 0,
 // 8-11 softmax group 1.
+//
+// Two instances. MAXK = 208 (L <= 208): as above. MAXK = 256 (208 < L <= 257): one tcgen05.mma has N <= 256 and a row
+// group owns 256 TMEM columns, so keys / query rows 0..255 run on the tensor cores exactly as above and the ONE token
+// beyond (ViT-L/14: 16 x 16 patches + CLS = 257) is folded in with scalar code:
+//   * extra key 256: every softmax thread adds s_x = q_row . k_256 (64 FMAs from smem) to its row max / row sum and
+//     p_x * v_256 to its O row before normalising;
+//   * extra query row 256: the otherwise idle warp 2 evaluates that single row against all 257 keys from the staged
+//     K / V tiles (lane = key for the scores, lane = two output columns for P V) and writes its 128 bytes itself.
+// That instance needs 2 x 99 KB of operand stages, so it writes O rows directly instead of staging them for TMA.
 #pragma once
 #include "gemm_tcgen05.cuh"  // pack2<>
 #include "ptx.cuh"
@@ -28,13 +38,44 @@
 namespace fsar {
 
 constexpr int ATT5_THREADS = 384;
-constexpr int ATT5_MAX_KEYS = 208;                       // 13 x 16; N of one tcgen05.mma must be <= 256
+constexpr int ATT5_MAX_KEYS = 208;                       // 13 x 16: the instance whose stages leave room for output staging
+constexpr int ATT5_MAX_TOKENS = 257;                     // 256 keys on the tensor cores + one scalar token (MAXK = 256)
 constexpr int ATT5_Q_BYTES = 2 * 128 * 128;              // two 128-row query tiles, 128 B (64 x 16-bit) per row
-constexpr int ATT5_KV_BYTES = ATT5_MAX_KEYS * 128;       // 26 KB, multiple of 1024
-constexpr int ATT5_STAGE_BYTES = ATT5_Q_BYTES + 2 * ATT5_KV_BYTES;
-constexpr int ATT5_OUT_TILE_BYTES = 32 * 128;             // output staging tile of one softmax warp: 32 rows x 128 B
-constexpr int ATT5_SMEM_BYTES = 2 * ATT5_STAGE_BYTES + 8 * ATT5_OUT_TILE_BYTES + 256 + 1024;
+constexpr int ATT5_OUT_TILE_BYTES = 32 * 128;            // output staging tile of one softmax warp: 32 rows x 128 B
 constexpr uint32_t ATT5_O_COL = 128;                     // O accumulator columns inside a group's 256-column region
+template <int MAXK>
+struct Att5Cfg {
+    static constexpr int KV_BYTES = MAXK * 128;                       // 26 KB / 32 KB, multiples of 1024
+    static constexpr int X_BYTES = (MAXK == 256) ? 3 * 1024 : 0;      // 8-row boxes of Q, K, V starting at token 256
+    static constexpr int STAGE_BYTES = ATT5_Q_BYTES + 2 * KV_BYTES + X_BYTES;
+    static constexpr bool STAGED_OUT = (MAXK == 208);
+    static constexpr int OUT_BYTES = STAGED_OUT ? 8 * ATT5_OUT_TILE_BYTES : 0;
+    static constexpr int SMEM_BYTES = 2 * STAGE_BYTES + OUT_BYTES + 256 + 1024;
+};
+
+// 16-bit row `row` of a 128B-swizzled [rows][64] tile -> 64 floats (chunk c of row r sits at ((c ^ (r & 7)) << 4))
+template <typename T16>
+__device__ __forceinline__ void att5_load_row(const uint8_t* tile, int row, float (&dst)[64]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint4 v = *reinterpret_cast<const uint4*>(tile + row * 128 + ((c ^ (row & 7)) << 4));
+        const T16* e = reinterpret_cast<const T16*>(&v);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) dst[c * 8 + t] = float(e[t]);
+    }
+}
+template <typename T16>
+__device__ __forceinline__ float att5_dot_row(const uint8_t* tile, int row, const float (&q)[64]) {
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint4 v = *reinterpret_cast<const uint4*>(tile + row * 128 + ((c ^ (row & 7)) << 4));
+        const T16* e = reinterpret_cast<const T16*>(&v);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) s = fmaf(q[c * 8 + t], float(e[t]), s);
+    }
+    return s;
+}
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -44,7 +85,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 struct Att5Params {
     int n_frames, L, heads, D;
-    int LK;          // keys padded to a multiple of 16
+    int Lm;          // tokens handled on the tensor cores: min(L, 256)
+    int extra;       // L - Lm (0 or 1): the scalar token of the MAXK = 256 instance
+    int LK;          // Lm padded to a multiple of 16
     int n_mtiles;    // 1 or 2 query tiles of 128 rows
     float scale_log2e;
     void* out;       // [n_frames * L, D] 16-bit (written through tmO)
@@ -55,15 +98,21 @@ struct Att5Params {
 
 // CAUSAL: query token i attends to keys 0..i only (the additive -inf upper-triangular mask of the CLIP text transformer,
 // few_shot.py:777-783); the frame encoder uses CAUSAL = false.
-template <typename T16, bool CAUSAL>
+template <typename T16, bool CAUSAL, int MAXK>
 __global__ void __launch_bounds__(ATT5_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                         const __grid_constant__ CUtensorMap tmO, const Att5Params p) {
+                         const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmO,
+                         const Att5Params p) {
+    using Cfg = Att5Cfg<MAXK>;
+    constexpr int ATT5_STAGE_BYTES = Cfg::STAGE_BYTES, ATT5_KV_BYTES = Cfg::KV_BYTES;
+    constexpr int X_OFF = ATT5_Q_BYTES + 2 * ATT5_KV_BYTES;      // Q | K | V rows of token 256 (1 KB each)
+    constexpr bool kExtra = (MAXK == 256);
+    static_assert(!(kExtra && CAUSAL), "the scalar extra token is not implemented for the causal instance");
     constexpr bool kBf16 = std::is_same<T16, __nv_bfloat16>::value;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* smem_out = smem + 2 * ATT5_STAGE_BYTES;      // 8 softmax warps x [32 rows][128 B]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + 8 * ATT5_OUT_TILE_BYTES);
+    uint8_t* smem_out = smem + 2 * ATT5_STAGE_BYTES;      // 8 softmax warps x [32 rows][128 B] (STAGED_OUT only)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + Cfg::OUT_BYTES);
     uint64_t* full_bar = bars;          // [2] TMA -> MMA
     uint64_t* empty_bar = bars + 2;     // [2] MMA -> TMA
     uint64_t* s_full = bars + 4;        // [2] per group: S ready
@@ -74,16 +123,18 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 
     const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
     const int n_items = p.n_frames * p.heads;
+    const bool extra = kExtra && p.extra != 0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
         tma_prefetch_desc(&tmKV);
-        tma_prefetch_desc(&tmO);
+        if (kExtra) tma_prefetch_desc(&tmX);
+        if (Cfg::STAGED_OUT) tma_prefetch_desc(&tmO);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], p.n_mtiles);   // one commit per row group
+            mbar_init(&empty_bar[i], p.n_mtiles + (extra ? 1 : 0));   // one commit per row group (+ the scalar-row warp)
             mbar_init(&s_full[i], 1);
             mbar_init(&p_full[i], 4);
             mbar_init(&o_full[i], 1);
@@ -104,7 +155,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (warp-uniform loop, elected lane)
-        const uint32_t bytes = uint32_t(p.n_mtiles) * 128 * 128 + 2u * uint32_t(p.LK) * 128;
+        const uint32_t bytes = uint32_t(p.n_mtiles) * 128 * 128 + 2u * uint32_t(p.LK) * 128 + (extra ? 3u * 1024u : 0u);
         int i = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
             const int s = i & 1;
@@ -119,6 +170,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                     tma_load_2d(st + g * 128 * 128, &tmQ, &full_bar[s], head * 64, frame * p.L + g * 128);
                 tma_load_2d(st + ATT5_Q_BYTES, &tmKV, &full_bar[s], p.D + head * 64, frame * p.L);
                 tma_load_2d(st + ATT5_Q_BYTES + ATT5_KV_BYTES, &tmKV, &full_bar[s], 2 * p.D + head * 64, frame * p.L);
+                if (extra) {   // token 256 (+ 7 rows nobody reads): its Q, K and V rows
+                    tma_load_2d(st + X_OFF, &tmX, &full_bar[s], head * 64, frame * p.L + 256);
+                    tma_load_2d(st + X_OFF + 1024, &tmX, &full_bar[s], p.D + head * 64, frame * p.L + 256);
+                    tma_load_2d(st + X_OFF + 2048, &tmX, &full_bar[s], 2 * p.D + head * 64, frame * p.L + 256);
+                }
             }
             __syncwarp();
         }
@@ -170,8 +226,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const int wq = warp & 3;              // TMEM lane quarter
         if (g < p.n_mtiles) {
             const int row = g * 128 + wq * 32 + lane;     // query token of this thread
-            const bool warp_valid = (g * 128 + wq * 32) < p.L;
-            const int n_keys = (CAUSAL && row + 1 < p.L) ? row + 1 : p.L;   // keys this query row may attend to
+            const bool warp_valid = (g * 128 + wq * 32) < p.Lm;
+            const int n_keys = (CAUSAL && row + 1 < p.Lm) ? row + 1 : p.Lm;   // (tensor-core) keys of this query row
             const uint32_t t_row = tmem_base + g * 256 + (uint32_t(wq * 32) << 16);
             const int n32 = p.LK / 32;             // full 32-column chunks of the score row
             const bool tail16 = (p.LK & 16) != 0;  // plus one 16-column chunk
@@ -182,13 +238,33 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
                 const uint32_t ip = i & 1;
                 const int it = p.reverse ? n_items - 1 - item : item;
-            const int frame = it / p.heads, head = it - frame * p.heads;
+                const int frame = it / p.heads, head = it - frame * p.heads;
                 float sum = 0.f;
                 mbar_wait(&s_full[g], ip);
                 tc_fence_after();
+                // scalar token 256 as a KEY: its score for this query row and its V row, straight from the staged tiles
+                // (they stay valid until this group's P V has been committed, i.e. until after the p_full arrival below)
+                float s_x = -INFINITY, p_x = 0.f;
+                uint4 vx[8];
+                if (extra && warp_valid) {
+                    const uint8_t* stg = smem + (i & 1) * ATT5_STAGE_BYTES;
+                    const uint8_t* q_tile = stg + g * 128 * 128;
+                    const int qr = wq * 32 + lane;
+                    s_x = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint4 qa = *reinterpret_cast<const uint4*>(q_tile + qr * 128 + ((c ^ (qr & 7)) << 4));
+                        const uint4 kb = *reinterpret_cast<const uint4*>(stg + X_OFF + 1024 + (c << 4));   // row 0: no swizzle
+                        const T16* qe = reinterpret_cast<const T16*>(&qa);
+                        const T16* ke = reinterpret_cast<const T16*>(&kb);
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) s_x = fmaf(float(qe[t]), float(ke[t]), s_x);
+                        vx[c] = *reinterpret_cast<const uint4*>(stg + X_OFF + 2048 + (c << 4));
+                    }
+                }
                 if (warp_valid) {
                     // ---- pass 1: row maximum (only the last chunk can contain padded keys >= L)
-                    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+                    float mx0 = s_x, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
                     if (FSAR_PROBE(p.debug, 1)) mx0 = 0.f;
                     for (int c = 0; c < (FSAR_PROBE(p.debug, 1) ? 0 : n32); ++c) {
                         uint32_t r[32];
@@ -265,6 +341,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                         }
                         tmem_st_32x32b_x8(t_row + n32 * 16, w);
                     }
+                    if (extra) {
+                        const float e_x = ex2_approx(fmaf(s_x, p.scale_log2e, -m_scaled));
+                        s3 += e_x;
+                        p_x = float(T16(e_x));      // rounded like the P operand of the tensor-core keys
+                    }
                     sum = (s0 + s1) + (s2 + s3);
                     tc_wait_st();
                 }
@@ -283,33 +364,118 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&o_empty[g]);
+                if (extra && warp_valid) {   // O row += p_x * v_256
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const T16* v0 = reinterpret_cast<const T16*>(&vx[c]);
+                        const T16* v1 = reinterpret_cast<const T16*>(&vx[4 + c]);
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            o0[8 * c + t] = __float_as_uint(fmaf(p_x, float(v0[t]), __uint_as_float(o0[8 * c + t])));
+                            o1[8 * c + t] = __float_as_uint(fmaf(p_x, float(v1[t]), __uint_as_float(o1[8 * c + t])));
+                        }
+                    }
+                }
                 if (warp_valid && !FSAR_PROBE(p.debug, 4)) {
-                    const float inv = 1.0f / sum;      // rows >= L: garbage, clipped by the TMA store
-                    if (lane == 0) tma_store_wait_read<0>();   // the previous item's store has drained the tile
-                    __syncwarp();
+                    const float inv = 1.0f / sum;      // rows >= L: garbage, clipped by the TMA store / skipped below
+                    uint4 v[8];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        st_shared_v4(out_row + ((uint32_t(j) ^ sw) << 4),
-                                     pack2<T16>(__uint_as_float(o0[8 * j]) * inv, __uint_as_float(o0[8 * j + 1]) * inv),
-                                     pack2<T16>(__uint_as_float(o0[8 * j + 2]) * inv, __uint_as_float(o0[8 * j + 3]) * inv),
-                                     pack2<T16>(__uint_as_float(o0[8 * j + 4]) * inv, __uint_as_float(o0[8 * j + 5]) * inv),
-                                     pack2<T16>(__uint_as_float(o0[8 * j + 6]) * inv, __uint_as_float(o0[8 * j + 7]) * inv));
+                    for (int j = 0; j < 4; ++j) {
+                        v[j].x = pack2<T16>(__uint_as_float(o0[8 * j]) * inv, __uint_as_float(o0[8 * j + 1]) * inv);
+                        v[j].y = pack2<T16>(__uint_as_float(o0[8 * j + 2]) * inv, __uint_as_float(o0[8 * j + 3]) * inv);
+                        v[j].z = pack2<T16>(__uint_as_float(o0[8 * j + 4]) * inv, __uint_as_float(o0[8 * j + 5]) * inv);
+                        v[j].w = pack2<T16>(__uint_as_float(o0[8 * j + 6]) * inv, __uint_as_float(o0[8 * j + 7]) * inv);
+                        v[4 + j].x = pack2<T16>(__uint_as_float(o1[8 * j]) * inv, __uint_as_float(o1[8 * j + 1]) * inv);
+                        v[4 + j].y = pack2<T16>(__uint_as_float(o1[8 * j + 2]) * inv, __uint_as_float(o1[8 * j + 3]) * inv);
+                        v[4 + j].z = pack2<T16>(__uint_as_float(o1[8 * j + 4]) * inv, __uint_as_float(o1[8 * j + 5]) * inv);
+                        v[4 + j].w = pack2<T16>(__uint_as_float(o1[8 * j + 6]) * inv, __uint_as_float(o1[8 * j + 7]) * inv);
+                    }
+                    if (Cfg::STAGED_OUT) {
+                        if (lane == 0) tma_store_wait_read<0>();   // the previous item's store has drained the tile
+                        __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        st_shared_v4(out_row + ((uint32_t(4 + j) ^ sw) << 4),
-                                     pack2<T16>(__uint_as_float(o1[8 * j]) * inv, __uint_as_float(o1[8 * j + 1]) * inv),
-                                     pack2<T16>(__uint_as_float(o1[8 * j + 2]) * inv, __uint_as_float(o1[8 * j + 3]) * inv),
-                                     pack2<T16>(__uint_as_float(o1[8 * j + 4]) * inv, __uint_as_float(o1[8 * j + 5]) * inv),
-                                     pack2<T16>(__uint_as_float(o1[8 * j + 6]) * inv, __uint_as_float(o1[8 * j + 7]) * inv));
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_3d(&tmO, out_tile, head * 64, g * 128 + wq * 32, frame);
-                        tma_store_commit();
+                        for (int j = 0; j < 8; ++j)
+                            st_shared_v4(out_row + ((uint32_t(j) ^ sw) << 4), v[j].x, v[j].y, v[j].z, v[j].w);
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_3d(&tmO, out_tile, head * 64, g * 128 + wq * 32, frame);
+                            tma_store_commit();
+                        }
+                    } else if (row < p.L) {
+                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<T16*>(p.out) +
+                                                              ((size_t)frame * p.L + row) * p.D + head * 64);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) dst[j] = v[j];
                     }
                 }
             }
-            if (lane == 0) tma_store_wait<0>();   // every output tile is globally written before the CTA retires
+            if (Cfg::STAGED_OUT && lane == 0) tma_store_wait<0>();   // output tiles are globally written before the CTA retires
+        }
+    } else if (warp == 2 && extra) {
+        // ------------------------------------------------------------ scalar token 256 as a QUERY row: one warp, all 257
+        // keys, from the staged tiles. Scores: lane = key (8 per lane); P V: lane = two output columns.
+        T16* out = reinterpret_cast<T16*>(p.out);
+        int i = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+            const int s = i & 1;
+            const uint32_t ph = (i >> 1) & 1;
+            const int it = p.reverse ? n_items - 1 - item : item;
+            const int frame = it / p.heads, head = it - frame * p.heads;
+            const uint8_t* stg = smem + s * ATT5_STAGE_BYTES;
+            const uint8_t* k_tile = stg + ATT5_Q_BYTES;
+            const uint8_t* v_tile = k_tile + ATT5_KV_BYTES;
+            mbar_wait(&full_bar[s], ph);
+            float q[64];
+            att5_load_row<T16>(stg + X_OFF, 0, q);
+            float sc[8];
+            float mx = att5_dot_row<T16>(stg + X_OFF + 1024, 0, q);   // key 256
+            const float s_x = mx;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                sc[t] = att5_dot_row<T16>(k_tile, lane + 32 * t, q);
+                mx = fmaxf(mx, sc[t]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            const float m_scaled = mx * p.scale_log2e;
+            float sum = 0.f;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const float e = ex2_approx(fmaf(sc[t], p.scale_log2e, -m_scaled));
+                sum += e;
+                sc[t] = float(T16(e));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float e_x = ex2_approx(fmaf(s_x, p.scale_log2e, -m_scaled));
+            sum += e_x;
+            const float p_x = float(T16(e_x));
+            const uint32_t col = uint32_t(lane >> 2), sub = uint32_t(lane & 3) * 4;   // 16-byte chunk / byte offset inside it
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+#pragma unroll 8
+                for (int src = 0; src < 32; ++src) {
+                    const int j = 32 * t + src;
+                    const float pj = __shfl_sync(0xffffffffu, sc[t], src);
+                    const uint32_t w = *reinterpret_cast<const uint32_t*>(v_tile + j * 128 + ((col ^ uint32_t(j & 7)) << 4) + sub);
+                    const T16* e = reinterpret_cast<const T16*>(&w);
+                    a0 = fmaf(pj, float(e[0]), a0);
+                    a1 = fmaf(pj, float(e[1]), a1);
+                }
+            }
+            {
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(stg + X_OFF + 2048 + (col << 4) + sub);
+                const T16* e = reinterpret_cast<const T16*>(&w);
+                a0 = fmaf(p_x, float(e[0]), a0);
+                a1 = fmaf(p_x, float(e[1]), a1);
+            }
+            const float inv = 1.0f / sum;
+            *reinterpret_cast<uint32_t*>(out + ((size_t)frame * p.L + 256) * p.D + head * 64 + 2 * lane) =
+                pack2<T16>(a0 * inv, a1 * inv);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);   // this warp no longer reads the stage
         }
     }
 

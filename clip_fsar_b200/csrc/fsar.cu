@@ -393,30 +393,39 @@ int attention(fsar_handle* h, const T16* qkv, int n_frames, int L, int heads, T1
             (double)n_frames * L * D * 2.0 * 4.0);
     if (causal && L > ATT5_MAX_KEYS)
         return fail(h, FSAR_E_INVALID, "causal attention supports at most %d tokens, got %d", ATT5_MAX_KEYS, L);
-    if (L <= ATT5_MAX_KEYS && (!h->legacy_attention || causal)) {
-        // tcgen05 / TMEM path: S and O accumulate in tensor memory, one softmax thread per query row
+    if (L <= ATT5_MAX_TOKENS && (!h->legacy_attention || causal)) {
+        // tcgen05 / TMEM path: S and O accumulate in tensor memory, one softmax thread per query row.
+        // L <= 208: MAXK = 208 instance (TMA-staged output); 208 < L <= 257: MAXK = 256 instance (ViT-L/14: 256 tokens
+        // on the tensor cores + one scalar token).
+        const bool big = L > ATT5_MAX_KEYS;
         static bool done5 = false;
         if (!done5) {
-            CU_OK(h, cudaFuncSetAttribute(attention_tcgen05_kernel<T16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          ATT5_SMEM_BYTES));
-            CU_OK(h, cudaFuncSetAttribute(attention_tcgen05_kernel<T16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          ATT5_SMEM_BYTES));
+            CU_OK(h, cudaFuncSetAttribute(attention_tcgen05_kernel<T16, false, 208>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Att5Cfg<208>::SMEM_BYTES));
+            CU_OK(h, cudaFuncSetAttribute(attention_tcgen05_kernel<T16, true, 208>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Att5Cfg<208>::SMEM_BYTES));
+            CU_OK(h, cudaFuncSetAttribute(attention_tcgen05_kernel<T16, false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Att5Cfg<256>::SMEM_BYTES));
             done5 = true;
         }
         Att5Params ap{};
         ap.n_frames = n_frames; ap.L = L; ap.heads = heads; ap.D = D;
-        ap.LK = round_up(L, 16); ap.n_mtiles = (L + 127) / 128; ap.scale_log2e = scale_log2e; ap.out = out; ap.reverse = reverse;
+        ap.Lm = L < 256 ? L : 256; ap.extra = L - ap.Lm;
+        ap.LK = round_up(ap.Lm, 16); ap.n_mtiles = (ap.Lm + 127) / 128; ap.scale_log2e = scale_log2e; ap.out = out; ap.reverse = reverse;
         { const char* e = getenv("FSAR_ATT_DEBUG"); ap.debug = e ? atoi(e) : 0; }
-        CUtensorMap tq, tkv, to;
+        CUtensorMap tq, tkv, tx, to;
         RET_IF(get_tmap(h, qkv, n_frames * L, 3 * D, 128, 64, 0, &tq));
         RET_IF(get_tmap(h, qkv, n_frames * L, 3 * D, ap.LK, 64, 0, &tkv));
+        RET_IF(get_tmap(h, qkv, n_frames * L, 3 * D, 8, 64, 0, &tx));
         RET_IF(get_tmap_tokens3d(h, out, n_frames, L, D, &to));
         const int items = n_frames * heads;
         const int grid5 = items < h->sms ? items : h->sms;
         if (causal)
-            launch_pdl(h, attention_tcgen05_kernel<T16, true>, dim3(grid5), dim3(ATT5_THREADS), ATT5_SMEM_BYTES, st, tq, tkv, to, ap);
+            launch_pdl(h, attention_tcgen05_kernel<T16, true, 208>, dim3(grid5), dim3(ATT5_THREADS), Att5Cfg<208>::SMEM_BYTES, st, tq, tkv, tx, to, ap);
+        else if (big)
+            launch_pdl(h, attention_tcgen05_kernel<T16, false, 256>, dim3(grid5), dim3(ATT5_THREADS), Att5Cfg<256>::SMEM_BYTES, st, tq, tkv, tx, to, ap);
         else
-            launch_pdl(h, attention_tcgen05_kernel<T16, false>, dim3(grid5), dim3(ATT5_THREADS), ATT5_SMEM_BYTES, st, tq, tkv, to, ap);
+            launch_pdl(h, attention_tcgen05_kernel<T16, false, 208>, dim3(grid5), dim3(ATT5_THREADS), Att5Cfg<208>::SMEM_BYTES, st, tq, tkv, tx, to, ap);
         return check_launch(h, "attention_tcgen05_kernel");
     }
     const dim3 grid((L + ATT_QROWS - 1) / ATT_QROWS, heads, n_frames);

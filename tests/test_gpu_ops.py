@@ -73,13 +73,36 @@ def test_gemm_rejects_bad_shapes(eng, lib):
         eng.op_gemm(torch.zeros(8, 64, device=DEV, dtype=dt), torch.zeros(12, 64, device=DEV, dtype=dt))   # N % 8
 
 
-@pytest.mark.parametrize("n,L,H", [(2, 5, 2), (3, 197, 2), (2, 197, 12), (2, 257, 4), (1, 64, 1), (1, 65, 1), (1, 1, 1)])
+# 197 = ViT-B/16, 257 = ViT-L/14 (256 tokens on the tensor cores + one scalar token), 208 / 209 / 256 = the instance
+# boundaries (MAXK = 208 with TMA-staged output, MAXK = 256 with direct output), 258+ = legacy mma.sync kernel
+@pytest.mark.parametrize("n,L,H", [(2, 5, 2), (3, 197, 2), (2, 197, 12), (2, 257, 4), (5, 257, 16), (1, 64, 1), (1, 65, 1), (1, 1, 1),
+                                   (2, 208, 2), (2, 209, 2), (3, 256, 3), (2, 129, 1), (2, 258, 2), (1, 272, 1)])
 def test_attention_core(eng, n, L, H):
     D = H * 64
     qkv = torch.randn(n * L, 3 * D, device=DEV).to(eng.operand_dtype)
     q, k, v = qkv.float().reshape(n, L, 3, H, 64).permute(2, 0, 3, 1, 4)
     ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1) @ v).transpose(1, 2).reshape(n * L, D)
-    assert rel_l2(eng.op_attention(qkv, n, L, H), ref) < 6e-4                  # 16-bit P and output rounding
+    out = eng.op_attention(qkv, n, L, H)
+    assert rel_l2(out, ref) < 6e-4                                             # 16-bit P and output rounding
+    # no row may be off (the scalar token of L = 257 is one row in 257: a global norm would hide it)
+    assert float((out.float().cpu() - ref.cpu()).abs().max()) < 2e-2 * float(ref.abs().max())
+
+
+def test_attention_core_sharp_rows(eng):
+    """Peaked softmax rows (large logits), L = 257: the scalar key must enter the row maximum, and rows whose mass sits
+    on the scalar key / whose query is the scalar row must come out right."""
+    n, L, H = 2, 257, 2
+    D = H * 64
+    qkv = torch.randn(n * L, 3 * D, device=DEV)
+    qkv[:, :2 * D] *= 3.0                                                       # logits ~ N(0, 9^2 * 64 / 64)
+    qkv = qkv.to(eng.operand_dtype)
+    q, k, v = qkv.float().reshape(n, L, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1) @ v).transpose(1, 2).reshape(n * L, D)
+    out = eng.op_attention(qkv, n, L, H).float().cpu()
+    assert torch.isfinite(out).all()
+    assert rel_l2(out, ref) < 2e-3
+    rows = ref.reshape(n, L, D)
+    assert rel_l2(out.reshape(n, L, D)[:, 256], rows[:, 256]) < 2e-3            # the scalar query row itself
 
 
 def test_attention_rejects_too_many_tokens(eng, lib):

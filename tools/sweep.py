@@ -7,8 +7,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from clip_fsar_b200 import lib as L, synth
 
-CASES = [("ViT-B/16", 5, 1, 8), ("ViT-B/16", 5, 5, 8), ("ViT-B/16", 5, 1, 16), ("ViT-B/16", 5, 1, 32), ("ViT-B/16", 10, 1, 8),
+CASES = [c for c in [("ViT-B/16", 5, 1, 8), ("ViT-B/16", 5, 5, 8), ("ViT-B/16", 5, 1, 16), ("ViT-B/16", 5, 1, 32), ("ViT-B/16", 10, 1, 8),
          ("ViT-B/16", 20, 1, 8), ("ViT-B/16", 10, 5, 16), ("ViT-B/16", 20, 5, 32), ("ViT-L/14", 5, 1, 16)]
+         if not os.environ.get("SWEEP_ONLY") or os.environ["SWEEP_ONLY"] == c[0]]
 
 def main():
     dev = torch.device("cuda", 0)
@@ -42,8 +43,11 @@ def main():
             logits, _ = eng.episode_forward(*args, n_train_classes=64)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
-        flops = frames * synth.vit_flops_per_frame(g)
-        print(json.dumps(dict(backbone=geom, way=way, shot=shot, frames_per_video=T, frames_per_episode=frames, merge_before=merge,
+        flops = frames * synth.vit_flops_per_frame(g)     # reference-equivalent FLOPs (every row of every block)
+        eng.profile_begin()
+        eng.episode_forward(*args, n_train_classes=64)
+        prof = {k: round(v["ms"], 3) for k, v in eng.profile_end().items() if v["ms"] > 0}
+        print(json.dumps(dict(kernel_ms=prof, backbone=geom, way=way, shot=shot, frames_per_video=T, frames_per_episode=frames, merge_before=merge,
                               ms_per_episode=ms, episodes_per_s=1000.0 / ms, vit_tflops=flops / ms / 1e9, finite=bool(torch.isfinite(logits).all()),
                               us_per_frame=ms * 1e3 / frames)), flush=True)
         eng.close(); del sup, tgt; torch.cuda.empty_cache()
