@@ -178,8 +178,8 @@ layernorm_kernel(const float* x, void* out, const float* __restrict__ gamma, con
 // ln_post(x[:, 0, :]) @ proj  (few_shot.py:683-686). proj is [D, E] fp32.
 // grid = (ceil(frames / FPC), E / FINAL_COLS); 256 threads = FINAL_COLS columns x FINAL_KSPLIT slices of the D reduction.
 constexpr int FINAL_FPC = 4;
-constexpr int FINAL_COLS = 64;
-constexpr int FINAL_KSPLIT = 256 / FINAL_COLS;
+constexpr int FINAL_COLS = 32;                    // 32 columns x 8 slices of the D reduction: short dependent-load chains
+constexpr int FINAL_KSPLIT = 256 / FINAL_COLS;    // (the kernel is latency-bound: 1.5 MB of weights, a few MFLOP per CTA)
 __global__ void __launch_bounds__(256)
 final_proj_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                   const float* __restrict__ proj, float* __restrict__ out, int n_frames, int tokens, int D, int E,
@@ -241,7 +241,7 @@ final_proj_kernel(const float* __restrict__ x, const float* __restrict__ gamma, 
 #pragma unroll
     for (int f = 0; f < FINAL_FPC; ++f) acc[f] = 0.f;
     if (e < E) {
-#pragma unroll 8
+#pragma unroll 16
         for (int d = dlo; d < dhi; ++d) {
             const float w = __ldg(proj + (size_t)d * E + e);
 #pragma unroll
