@@ -36,6 +36,11 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library chatter)
+# is redirected to stderr; the line itself goes to a private duplicate of the original stdout.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
 from clip_fsar_b200 import synth  # noqa: E402
 
 WAY, SHOT, QPC, T, GEOM = 5, 1, 1, 8, "ViT-B/16"
@@ -146,7 +151,7 @@ def reference_arm(args, rank, world):
             "cpu_baseline": {"value": eps, "unit": "episodes/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": eps, "unit": "episodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def main():
@@ -333,7 +338,7 @@ def main():
                                       "note": "last block: Q / out_proj / ln_2 / MLP on the CLS row only (the only row "
                                               "ln_post reads); rates use executed FLOPs"},
             "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
