@@ -289,7 +289,8 @@ def main():
             traffic = sum(v["dram_bytes_per_launch"] * v["launches"] for v in gk) / sum(v["launches"] for v in gk)
     except (OSError, KeyError, ValueError):
         pass
-    roofline = {"bound": "tensor", "kernel": "gemm_tn_tcgen05_kernel (patch/QKV/out/fc1/fc2 epilogues)",
+    roofline = {"bound": "tensor", "kernel": "gemm_tn_tcgen05_pair_kernel, full-size launches (patch/QKV/out/fc1/fc2 epilogues over all "
+                                             "token rows; the n_frames-row launches of the CLS-only last block are class last_block_cls)",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
                 "peak_source": pk["src"] + " cuBLAS bf16, sustained (kernel timed inside a long step)",
                 "traffic": traffic, "traffic_source": "profiles/ncu_traffic.json (ncu --set full, mean over the GEMM launches)",
@@ -320,7 +321,7 @@ def main():
     # EXECUTES fewer in the last block, where only the CLS row is read downstream. Rates are quoted on
     # executed FLOPs (summed over the launches actually made), never on the skipped ones.
     flops_ref = 80 * synth.vit_flops_per_frame(g)
-    flops_ep = sum(prof[k]["flops"] for k in prof if k.startswith("gemm_") or k in ("attention", "final_proj")) / NP
+    flops_ep = sum(prof[k]["flops"] for k in prof if k.startswith("gemm_") or k in ("attention", "final_proj", "last_block_cls")) / NP
     line = {"metric": METRIC, "value": value, "unit": "episodes/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp16 operands / fp32 accumulate (reference: f32)", "data": "synthetic",

@@ -667,20 +667,20 @@ int vit_encode_gathered(fsar_handle* h, int n, float* feats_out, cudaStream_t st
             const float* b_in = W32(h, pre + "attn.in_proj_bias");
             T16* kv16 = h->qkv16;   // [M, 2 D]
             RET_IF(gemm(h, FSAR_K_GEMM_QKV, h->ln16, w_in + (size_t)D * D, b_in + D, kv16, M, 2 * D, D, EPI_STORE16, st, dir));
-            RET_IF(gemm(h, FSAR_K_GEMM_QKV, h->ln16, w_in, b_in, h->cls_q16, n, D, D, EPI_STORE16, st, 0, cls_pitch));
+            RET_IF(gemm(h, FSAR_K_LAST_BLOCK_CLS, h->ln16, w_in, b_in, h->cls_q16, n, D, D, EPI_STORE16, st, 0, cls_pitch));
             {
-                Scope s(h, st, FSAR_K_ATTENTION, 4.0 * n * c.heads * (double)L * ATT_HD, (double)M * 2 * D * 2.0);
+                Scope s(h, st, FSAR_K_LAST_BLOCK_CLS, 4.0 * n * c.heads * (double)L * ATT_HD, (double)M * 2 * D * 2.0);
                 launch_pdl(h, cls_attention_kernel<T16>, dim3(c.heads, n), dim3(128), 0, st, (const T16*)h->cls_q16,
                            (const T16*)kv16, h->cls_att16, L, D, 0.125f * 1.4426950408889634f);
                 RET_IF(check_launch(h, "cls_attention_kernel"));
             }
-            RET_IF(gemm(h, FSAR_K_GEMM_OUT, h->cls_att16, W16(h, pre + "attn.out_proj.weight"),
+            RET_IF(gemm(h, FSAR_K_LAST_BLOCK_CLS, h->cls_att16, W16(h, pre + "attn.out_proj.weight"),
                         W32(h, pre + "attn.out_proj.bias"), h->x32, n, D, D, EPI_RESID32, st, 0, 0, cls_pitch));
             RET_IF(layernorm(h, h->x32, h->cls_ln16, W32(h, pre + "ln_2.weight"), W32(h, pre + "ln_2.bias"), n, D, true, false,
-                             L, nullptr, nullptr, st, FSAR_K_LAYERNORM, 0, cls_pitch));
-            RET_IF(gemm(h, FSAR_K_GEMM_FC1, h->cls_ln16, W16(h, pre + "mlp.c_fc.weight"), W32(h, pre + "mlp.c_fc.bias"),
+                             L, nullptr, nullptr, st, FSAR_K_LAST_BLOCK_CLS, 0, cls_pitch));
+            RET_IF(gemm(h, FSAR_K_LAST_BLOCK_CLS, h->cls_ln16, W16(h, pre + "mlp.c_fc.weight"), W32(h, pre + "mlp.c_fc.bias"),
                         h->cls_h16, n, 4 * D, D, EPI_QGELU16, st));
-            RET_IF(gemm(h, FSAR_K_GEMM_FC2, h->cls_h16, W16(h, pre + "mlp.c_proj.weight"), W32(h, pre + "mlp.c_proj.bias"),
+            RET_IF(gemm(h, FSAR_K_LAST_BLOCK_CLS, h->cls_h16, W16(h, pre + "mlp.c_proj.weight"), W32(h, pre + "mlp.c_proj.bias"),
                         h->x32, n, D, 4 * D, EPI_RESID32, st, 0, 0, cls_pitch));
             break;
         }
@@ -950,7 +950,7 @@ int fsar_version(void) { return FSAR_VERSION; }
 const char* fsar_class_name(int k) {
     static const char* names[FSAR_PROF_CLASSES] = {"patch_gather", "gemm_patch", "layernorm", "gemm_qkv", "attention",
                                                    "gemm_out", "gemm_fc1", "gemm_fc2", "final_proj", "head_misc",
-                                                   "modulator", "cos_otam"};
+                                                   "modulator", "cos_otam", "last_block_cls"};
     return (k >= 0 && k < FSAR_PROF_CLASSES) ? names[k] : "?";
 }
 

@@ -14,7 +14,7 @@ LIB_NAME = "libfsar_sm100.so"
 # FSAR_LIB_PATH selects another build of the same sources (e.g. the -DFSAR_BF16 operand-type variant)
 LIB_PATH = os.environ.get("FSAR_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
-FSAR_PROF_CLASSES = 12
+FSAR_PROF_CLASSES = 13
 EPI_STORE16, EPI_QGELU16, EPI_RESID32, EPI_PATCH32, EPI_STORE32 = 0, 1, 2, 3, 4
 
 # every symbol include/fsar.h declares (tests check the library exports exactly these)

@@ -81,7 +81,7 @@ typedef struct fsar_episode {
 } fsar_episode;
 
 /* Per-kernel-class device time of the calls issued between fsar_profile_begin/end (CUDA events on `stream`). */
-#define FSAR_PROF_CLASSES 12
+#define FSAR_PROF_CLASSES 13
 typedef struct fsar_profile {
     double ms[FSAR_PROF_CLASSES];        /* summed device milliseconds */
     int64_t launches[FSAR_PROF_CLASSES]; /* kernel launches */
@@ -91,7 +91,8 @@ typedef struct fsar_profile {
 enum {
     FSAR_K_PATCH_GATHER = 0, FSAR_K_GEMM_PATCH = 1, FSAR_K_LAYERNORM = 2, FSAR_K_GEMM_QKV = 3,
     FSAR_K_ATTENTION = 4, FSAR_K_GEMM_OUT = 5, FSAR_K_GEMM_FC1 = 6, FSAR_K_GEMM_FC2 = 7,
-    FSAR_K_FINAL_PROJ = 8, FSAR_K_HEAD_MISC = 9, FSAR_K_MODULATOR = 10, FSAR_K_COS_OTAM = 11
+    FSAR_K_FINAL_PROJ = 8, FSAR_K_HEAD_MISC = 9, FSAR_K_MODULATOR = 10, FSAR_K_COS_OTAM = 11,
+    FSAR_K_LAST_BLOCK_CLS = 12   /* last block, CLS rows only: Q / out_proj / fc1 / fc2 GEMMs over n_frames rows, CLS attention, ln_2 */
 };
 
 int fsar_version(void);

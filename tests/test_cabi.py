@@ -33,7 +33,8 @@ def test_config_struct_layout(lib):
     # 17 x 4-byte fields, in header order
     assert ctypes.sizeof(lib.FsarConfig) == 68
     assert ctypes.sizeof(lib.FsarEpisode) == 4 * 8 + 8 * 4
-    assert ctypes.sizeof(lib.FsarProfile) == 12 * 8 * 4
+    assert ctypes.sizeof(lib.FsarProfile) == 13 * 8 * 4 and lib.FSAR_PROF_CLASSES == 13
+    assert ctypes.sizeof(lib.FsarTextConfig) == 20
 
 
 def test_library_has_no_driver_link_dependency(lib):
