@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <set>
 #include <string>
 #include <tuple>
 #include <unordered_map>
@@ -115,6 +116,7 @@ struct fsar_handle {
                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     EncodeFn encode = nullptr;
     std::map<std::tuple<const void*, int, int, int, long long>, CUtensorMap> tmaps;
+    std::set<const void*> smem_opt_in;   // kernels whose dynamic smem limit has been raised on this handle's device
     // ---- host-buffer path
     HostSlot slot[2];
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
@@ -265,17 +267,24 @@ int get_tmap_tokens3d(fsar_handle* h, const void* ptr, int n_frames, int L, int 
     return 0;
 }
 
+// Opt a kernel into more than 48 KB of dynamic shared memory, once per handle (the attribute is per device, and two
+// handles of one process may sit on different devices).
+template <typename Kernel>
+int ensure_smem(fsar_handle* h, Kernel kern, int bytes) {
+    const void* key = reinterpret_cast<const void*>(kern);
+    if (h->smem_opt_in.count(key)) return 0;
+    CU_OK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    h->smem_opt_in.insert(key);
+    return 0;
+}
+
 // ---------------------------------------------------------------- GEMM dispatch
 template <int BN, int EPI>
 int launch_gemm_inst(fsar_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                      const GemmParams& p, cudaStream_t st) {
     typedef GemmCfg<BN> Cfg;
     auto kern = gemm_tn_tcgen05_kernel<BN, EPI, T16>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        CU_OK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_done = true;
-    }
+    RET_IF(ensure_smem(h, kern, Cfg::SMEM_BYTES));
     const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (p.N + BN - 1) / BN;
     const int tiles = m_tiles * n_tiles;
     const int grid = tiles < h->sms ? tiles : h->sms;
@@ -287,11 +296,7 @@ template <int EPI>
 int launch_gemm_pair_inst(fsar_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                           const GemmParams& p, cudaStream_t st) {
     auto kern = gemm_tn_tcgen05_pair_kernel<EPI, T16>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        CU_OK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
-        attr_done = true;
-    }
+    RET_IF(ensure_smem(h, kern, GEMM2_SMEM_BYTES));
     const int tiles = ((p.M + 255) / 256) * ((p.N + GEMM2_BN - 1) / GEMM2_BN);
     const int pairs = tiles < h->sms / 2 ? tiles : h->sms / 2;
     launch_pdl(h, kern, dim3(2 * pairs), dim3(GEMM_THREADS), GEMM2_SMEM_BYTES, st, ta, tb, tc, p);   // __cluster_dims__(2, 1, 1)
@@ -398,16 +403,9 @@ int attention(fsar_handle* h, const T16* qkv, int n_frames, int L, int heads, T1
         // L <= 208: MAXK = 208 instance (TMA-staged output); 208 < L <= 257: MAXK = 256 instance (ViT-L/14: 256 tokens
         // on the tensor cores + one scalar token).
         const bool big = L > ATT5_MAX_KEYS;
-        static bool done5 = false;
-        if (!done5) {
-            CU_OK(h, cudaFuncSetAttribute(attention_tcgen05_kernel<T16, false, 208>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          Att5Cfg<208>::SMEM_BYTES));
-            CU_OK(h, cudaFuncSetAttribute(attention_tcgen05_kernel<T16, true, 208>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          Att5Cfg<208>::SMEM_BYTES));
-            CU_OK(h, cudaFuncSetAttribute(attention_tcgen05_kernel<T16, false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          Att5Cfg<256>::SMEM_BYTES));
-            done5 = true;
-        }
+        RET_IF(ensure_smem(h, attention_tcgen05_kernel<T16, false, 208>, Att5Cfg<208>::SMEM_BYTES));
+        RET_IF(ensure_smem(h, attention_tcgen05_kernel<T16, true, 208>, Att5Cfg<208>::SMEM_BYTES));
+        RET_IF(ensure_smem(h, attention_tcgen05_kernel<T16, false, 256>, Att5Cfg<256>::SMEM_BYTES));
         Att5Params ap{};
         ap.n_frames = n_frames; ap.L = L; ap.heads = heads; ap.D = D;
         ap.Lm = L < 256 ? L : 256; ap.extra = L - ap.Lm;
@@ -430,20 +428,10 @@ int attention(fsar_handle* h, const T16* qkv, int n_frames, int L, int heads, T1
     }
     const dim3 grid((L + ATT_QROWS - 1) / ATT_QROWS, heads, n_frames);
     if (L <= 208) {
-        static bool done = false;
-        if (!done) {
-            CU_OK(h, cudaFuncSetAttribute(attention_mma_kernel<T16, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          att_smem_bytes<13>()));
-            done = true;
-        }
+        RET_IF(ensure_smem(h, attention_mma_kernel<T16, 13>, att_smem_bytes<13>()));
         launch_pdl(h, attention_mma_kernel<T16, 13>, grid, dim3(128), att_smem_bytes<13>(), st, qkv, out, L, D, scale_log2e);
     } else if (L <= 272) {
-        static bool done = false;
-        if (!done) {
-            CU_OK(h, cudaFuncSetAttribute(attention_mma_kernel<T16, 17>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          att_smem_bytes<17>()));
-            done = true;
-        }
+        RET_IF(ensure_smem(h, attention_mma_kernel<T16, 17>, att_smem_bytes<17>()));
         launch_pdl(h, attention_mma_kernel<T16, 17>, grid, dim3(128), att_smem_bytes<17>(), st, qkv, out, L, D, scale_log2e);
     } else {
         return fail(h, FSAR_E_INVALID, "attention: %d tokens per frame exceeds the supported 272", L);
@@ -457,7 +445,7 @@ int linear_f32(fsar_handle* h, const float* A, const float* W, const float* bias
     const dim3 grid((N + LIN_BN - 1) / LIN_BN, (R + LIN_BM - 1) / LIN_BM);
     Scope s(h, st, FSAR_K_MODULATOR, 2.0 * R * N * K, 4.0 * ((double)N * K + (double)R * K + (double)R * N));
     if ((K % (LIN_BK * LIN_WARPS)) != 0) return fail(h, FSAR_E_INVALID, "linear: K=%d must be a multiple of %d", K, LIN_BK * LIN_WARPS);
-    linear_f32_kernel<ACT><<<grid, LIN_THREADS, 0, st>>>(A, W, bias, residual, C, R, N, K);
+    launch_pdl(h, linear_f32_kernel<ACT>, dim3(grid), dim3(LIN_THREADS), 0, st, A, W, bias, residual, C, R, N, K);
     return check_launch(h, "linear_f32_kernel");
 }
 
@@ -770,7 +758,7 @@ int modulate_rows(fsar_handle* h, HeadWs& w, const float* x, int n_q, int n_s, i
             const int nmax = T + 1, dh = c.mod_dim_head;
             const size_t smem = sizeof(float) * ((size_t)3 * nmax * dh + (size_t)nmax * (nmax + 1));
             Scope s(h, st, FSAR_K_MODULATOR, 4.0 * rows * nmax * inner, 4.0 * 4.0 * rows * inner);
-            modulator_attention_kernel<<<dim3(n_q + n_s, c.mod_heads), 128, smem, st>>>(
+            launch_pdl(h, modulator_attention_kernel, dim3(n_q + n_s, c.mod_heads), dim3(128), smem, st, 
                 w.mod_qkvbuf, w.mod_qkvbuf + inner, w.mod_qkvbuf + 2 * inner, w.mod_att, n_q, T, 3 * inner, inner, dh,
                 1.0f / sqrtf((float)dh));
             RET_IF(check_launch(h, "modulator_attention_kernel"));
@@ -791,7 +779,7 @@ int otam_logits(fsar_handle* h, const float* q, const float* protos, int Q, int 
     if (T > OTAM_MAX_T || T < 1) return fail(h, FSAR_E_INVALID, "otam: T=%d outside [1, %d]", T, OTAM_MAX_T);
     Scope s(h, st, FSAR_K_COS_OTAM, 2.0 * Q * way * T * T * h->cfg.embed_dim,
             4.0 * ((double)(Q + way) * T * h->cfg.embed_dim + (double)Q * way));
-    cos_otam_kernel<<<dim3(Q, way), 256, 0, st>>>(q, protos, T, h->cfg.embed_dim, way, h->cfg.otam_lambda, single_direct,
+    launch_pdl(h, cos_otam_kernel, dim3(Q, way), dim3(256), 0, st, q, protos, T, h->cfg.embed_dim, way, h->cfg.otam_lambda, single_direct,
                                                   logits, dists, cum);
     return check_launch(h, "cos_otam_kernel");
 }
@@ -810,12 +798,12 @@ int head_forward(fsar_handle* h, HeadWs& w, const float* sup, const float* tgt, 
     }
     {
         Scope s(h, st, FSAR_K_HEAD_MISC, 0.0, 8.0 * S);
-        class_index_kernel<<<1, 128, 0, st>>>(support_labels, S, w.cls, w.counts, way);
+        launch_pdl(h, class_index_kernel, dim3(1), dim3(128), 0, st, support_labels, S, w.cls, w.counts, way);
         RET_IF(check_launch(h, "class_index_kernel"));
     }
     if (text_mode == 1) {   // TRAIN.EVAL_TEXT: text probabilities only, the modulator / OTAM are not evaluated
         Scope s(h, st, FSAR_K_HEAD_MISC, 2.0 * Q * way * E, 4.0 * ((double)Q * T * E + (double)way * E));
-        text_fusion_kernel<<<Q, 256, sizeof(float) * E, st>>>(tgt, W32(h, "text_features_test"), real_support_labels, w.cls,
+        launch_pdl(h, text_fusion_kernel, dim3(Q), dim3(256), sizeof(float) * E, st, tgt, W32(h, "text_features_test"), real_support_labels, w.cls,
                                                               w.counts, S, T, E, way, W32(h, "scale"), 1, 0.f, nullptr, logits);
         RET_IF(check_launch(h, "text_fusion_kernel"));
         h->last_S = S; h->last_Q = Q; h->last_T = T; h->last_way = way; h->last_rows = 0;
@@ -826,7 +814,7 @@ int head_forward(fsar_handle* h, HeadWs& w, const float* sup, const float* tgt, 
         if (!find_w(h, "text_features_train")->set) return fail(h, FSAR_E_STATE, "text_features_train has not been set");
         Scope s(h, st, FSAR_K_HEAD_MISC, 2.0 * (S + Q) * h->n_text_train * E,
                 4.0 * ((double)(S + Q) * T * E + (double)h->n_text_train * E));
-        class_text_logits_kernel<<<S + Q, 256, sizeof(float) * E, st>>>(sup, S, tgt, Q, T, E, W32(h, "text_features_train"),
+        launch_pdl(h, class_text_logits_kernel, dim3(S + Q), dim3(256), sizeof(float) * E, st, sup, S, tgt, Q, T, E, W32(h, "text_features_train"),
                                                                         h->n_text_train, W32(h, "scale"), class_logits);
         RET_IF(check_launch(h, "class_text_logits_kernel"));
     }
@@ -834,7 +822,7 @@ int head_forward(fsar_handle* h, HeadWs& w, const float* sup, const float* tgt, 
     const int rows = Q * T + n_sup_seq * (T + 1);
     {
         Scope s(h, st, FSAR_K_HEAD_MISC, 0.0, 8.0 * rows * E);
-        build_sequences_kernel<<<rows, 128, 0, st>>>(sup, tgt, W32(h, "text_features_test"), real_support_labels, w.cls,
+        launch_pdl(h, build_sequences_kernel, dim3(rows), dim3(128), 0, st, sup, tgt, W32(h, "text_features_test"), real_support_labels, w.cls,
                                                      w.counts, S, Q, T, E, way, merge_before, w.seq);
         RET_IF(check_launch(h, "build_sequences_kernel"));
     }
@@ -843,14 +831,14 @@ int head_forward(fsar_handle* h, HeadWs& w, const float* sup, const float* tgt, 
     RET_IF(modulate_rows(h, w, w.seq, Q, n_sup_seq, T, w.mod_out, st));
     {
         Scope s(h, st, FSAR_K_HEAD_MISC, 0.0, 8.0 * way * T * E);
-        prototype_kernel<<<way * T, 128, 0, st>>>(w.mod_out, Q * T, n_sup_seq, T, E, w.cls, w.counts, merge_before,
+        launch_pdl(h, prototype_kernel, dim3(way * T), dim3(128), 0, st, w.mod_out, Q * T, n_sup_seq, T, E, w.cls, w.counts, merge_before,
                                                   w.protos);
         RET_IF(check_launch(h, "prototype_kernel"));
     }
     RET_IF(otam_logits(h, w.mod_out, w.protos, Q, way, T, single_direct, logits, w.dists, w.cum, st));
     if (text_mode == 2) {   // TRAIN.COMBINE: geometric fusion of text and visual probabilities overwrites the logits
         Scope s(h, st, FSAR_K_HEAD_MISC, 2.0 * Q * way * E, 4.0 * ((double)Q * T * E + (double)way * E));
-        text_fusion_kernel<<<Q, 256, sizeof(float) * E, st>>>(tgt, W32(h, "text_features_test"), real_support_labels, w.cls,
+        launch_pdl(h, text_fusion_kernel, dim3(Q), dim3(256), sizeof(float) * E, st, tgt, W32(h, "text_features_test"), real_support_labels, w.cls,
                                                               w.counts, S, T, E, way, W32(h, "scale"), 2, text_coff, w.cum,
                                                               logits);
         RET_IF(check_launch(h, "text_fusion_kernel"));

@@ -21,6 +21,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Single CTA; S is small (way * shot).
 __global__ void class_index_kernel(const float* __restrict__ labels, int S, int* __restrict__ cls,
                                    int* __restrict__ counts, int way) {
+    pdl_trigger();   // programmatic dependent launch: see ptx.cuh
+    pdl_wait();
     for (int c = threadIdx.x; c < way; c += blockDim.x) counts[c] = 0;
     __syncthreads();
     for (int s = threadIdx.x; s < S; s += blockDim.x) {
@@ -47,6 +49,8 @@ __global__ void __launch_bounds__(256)
 class_text_logits_kernel(const float* __restrict__ sup, int S, const float* __restrict__ tgt, int Q, int T, int E,
                          const float* __restrict__ text, int C, const float* __restrict__ scale,
                          float* __restrict__ out) {
+    pdl_trigger();   // programmatic dependent launch: see ptx.cuh
+    pdl_wait();
     extern __shared__ float sm[];  // [E]
     __shared__ float red[8];
     const int vid = blockIdx.x;
@@ -91,6 +95,8 @@ __global__ void __launch_bounds__(128)
 build_sequences_kernel(const float* __restrict__ sup, const float* __restrict__ tgt, const float* __restrict__ text_test,
                        const float* __restrict__ real_labels, const int* __restrict__ cls, const int* __restrict__ counts,
                        int S, int Q, int T, int E, int way, int merge_before, float* __restrict__ seq) {
+    pdl_trigger();   // programmatic dependent launch: see ptx.cuh
+    pdl_wait();
     const int row = blockIdx.x;
     const int qrows = Q * T;
     float* dst = seq + (size_t)row * E;
@@ -134,6 +140,8 @@ template <int ACT>
 __global__ void __launch_bounds__(LIN_THREADS)
 linear_f32_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
                   const float* residual, float* C, int R, int N, int K) {
+    pdl_trigger();   // programmatic dependent launch: see ptx.cuh
+    pdl_wait();
     __shared__ __align__(16) float sA[LIN_WARPS][LIN_BK][LIN_BM + 4];   // [warp][k][row]
     __shared__ __align__(16) float sW[LIN_WARPS][LIN_BK][LIN_BN + 4];   // [warp][k][col]
     const int r0 = blockIdx.y * LIN_BM, n0 = blockIdx.x * LIN_BN;
@@ -229,6 +237,8 @@ constexpr int MOD_MAX_TOK = 40;
 __global__ void __launch_bounds__(128)
 modulator_attention_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                            float* __restrict__ o, int n_q_seq, int T, int pitch, int inner, int dh, float scale) {
+    pdl_trigger();   // programmatic dependent launch: see ptx.cuh
+    pdl_wait();
     extern __shared__ float sm[];  // q[n][dh], k[n][dh], v[n][dh], p[n][n+1]
     const int seq = blockIdx.x, head = blockIdx.y;
     int row0, n;
@@ -274,6 +284,8 @@ modulator_attention_kernel(const float* __restrict__ q, const float* __restrict_
 __global__ void __launch_bounds__(128)
 prototype_kernel(const float* __restrict__ mod_out, int q_rows, int n_sup_seq, int T, int E, const int* __restrict__ cls,
                  const int* __restrict__ counts, int merge_before, float* __restrict__ protos) {
+    pdl_trigger();   // programmatic dependent launch: see ptx.cuh
+    pdl_wait();
     const int c = blockIdx.x / T, t = blockIdx.x - c * T;
     float* dst = protos + ((size_t)c * T + t) * E;
     if (merge_before) {
@@ -334,6 +346,8 @@ text_fusion_kernel(const float* __restrict__ tgt /*[Q,T,E]*/, const float* __res
                    const float* __restrict__ real_labels, const int* __restrict__ cls, const int* __restrict__ counts,
                    int S, int T, int E, int way, const float* __restrict__ scale, int mode, float text_coff,
                    const float* __restrict__ cum_visual /*[Q,way] or null*/, float* __restrict__ logits /*[Q,way]*/) {
+    pdl_trigger();   // programmatic dependent launch: see ptx.cuh
+    pdl_wait();
     extern __shared__ float sm[];   // img[E]
     __shared__ float red[8];
     __shared__ float lg[TEXT_MAX_WAY];
@@ -434,6 +448,8 @@ __global__ void __launch_bounds__(256)
 cos_otam_kernel(const float* __restrict__ qf /*[Q,T,E]*/, const float* __restrict__ pf /*[way,T,E]*/, int T, int E,
                 int way, float lbda, int single_direct, float* __restrict__ logits /*[Q,way]*/,
                 float* __restrict__ dists_out /*[Q,way,T,T] or null*/, float* __restrict__ cum_out /*[Q,way] or null*/) {
+    pdl_trigger();   // programmatic dependent launch: see ptx.cuh
+    pdl_wait();
     __shared__ float sd[OTAM_MAX_T * OTAM_MAX_T];
     __shared__ float sqn[OTAM_MAX_T], spn[OTAM_MAX_T];
     __shared__ float sc[2][OTAM_MAX_T * (OTAM_MAX_T + 2)];
