@@ -11,11 +11,14 @@ GEOMETRIES = {
     # name: image, patch, width, layers, heads, embed
     "ViT-B/16": dict(image_size=224, patch_size=16, width=768, layers=12, heads=12, embed_dim=512),
     "ViT-L/14": dict(image_size=224, patch_size=14, width=1024, layers=24, heads=16, embed_dim=768),
+    "ViT-B/32": dict(image_size=224, patch_size=32, width=768, layers=12, heads=12, embed_dim=512),
     # small towers with the same structure, for tests that must finish in seconds on CPU
     "tiny": dict(image_size=32, patch_size=16, width=128, layers=2, heads=2, embed_dim=128),
     "small": dict(image_size=64, patch_size=16, width=256, layers=3, heads=4, embed_dim=256),
     # ViT-L/14 token / width geometry (257 tokens, width 1024, patch K = 588) with 2 layers, for parity tests
     "l14-2layer": dict(image_size=224, patch_size=14, width=1024, layers=2, heads=16, embed_dim=768),
+    # ViT-B/32 token geometry (50 tokens, patch K = 3072) with 2 layers
+    "b32-2layer": dict(image_size=224, patch_size=32, width=768, layers=2, heads=12, embed_dim=512),
 }
 
 
@@ -24,6 +27,7 @@ GEOMETRIES = {
 TEXT_GEOMETRIES = {
     "ViT-B/16": dict(width=512, layers=12, heads=8, context_length=77, vocab_size=49408),
     "ViT-L/14": dict(width=768, layers=12, heads=12, context_length=77, vocab_size=49408),
+    "ViT-B/32": dict(width=512, layers=12, heads=8, context_length=77, vocab_size=49408),
     "tiny": dict(width=128, layers=2, heads=2, context_length=77, vocab_size=49408),
     "small": dict(width=256, layers=3, heads=4, context_length=77, vocab_size=49408),
 }

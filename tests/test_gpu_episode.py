@@ -98,12 +98,14 @@ def test_episode_matches_16bit_emulating_oracle_tightly(lib, name):
     e.close()
 
 
-def test_vit_l14_geometry_against_oracle(lib):
-    """BASELINE.json configs[3] names ViT-L/14 (257 tokens, width 1024, 14x14 patches -> K = 588 padded to 640):
-    the reference head has no branch for it, so the oracle restatement is the checker."""
+@pytest.mark.parametrize("geom", ["l14-2layer", "b32-2layer"])
+def test_other_clip_geometries_against_oracle(lib, geom):
+    """BASELINE.json configs[3] names ViT-L/14 (257 tokens, width 1024, 14x14 patches -> K = 588 padded to 640; the
+    tcgen05 attention instance with the scalar 257th token); ViT-B/32 has 50 tokens and a 3072-deep patch GEMM. The
+    reference head has no branch for either, so the oracle restatement is the checker."""
     from clip_fsar_b200 import synth
     from oracle import fsar_oracle as O
-    g = synth.full_geometry("l14-2layer")
+    g = synth.full_geometry(geom)
     sd = synth.synth_state_dict(g, 3)
     e = lib.Engine(**dict(g, max_frames=6, max_videos=4, max_tokens=4, max_classes=8, otam_lambda=0.5, device=0))
     e.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
