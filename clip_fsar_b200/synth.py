@@ -206,6 +206,25 @@ def synth_episode(way=5, shot=1, queries_per_class=1, n_frames=8, image_size=224
     }
 
 
+def ragged_support(task, n_frames, keep_counts):
+    """Unequal shots per class (the reference averages whatever members a class has, few_shot.py:2949-2962): keep only
+    the first keep_counts[c] support videos of class c, in their (shuffled) order of appearance."""
+    labels = task["support_labels"].astype(np.int64)
+    seen = {}
+    keep = []
+    for i, c in enumerate(labels):
+        seen[c] = seen.get(c, 0) + 1
+        if seen[c] <= keep_counts[c]:
+            keep.append(i)
+    keep = np.array(keep)
+    out = dict(task)
+    frames = task["support_set"].reshape(len(labels), n_frames, *task["support_set"].shape[1:])
+    out["support_set"] = np.ascontiguousarray(frames[keep].reshape(-1, *task["support_set"].shape[1:]))
+    out["support_labels"] = np.ascontiguousarray(task["support_labels"][keep])
+    out["real_support_labels"] = np.ascontiguousarray(task["real_support_labels"][keep])
+    return out
+
+
 def synth_raw_frames(n_frames, height, width, seed=77):
     """uint8 [n, H, W, 3] "camera" frames (8x8 blocks plus noise, so interpolation errors are visible) for the
     pre-processing path; regenerated from the seed by tests instead of being stored in the fixtures."""

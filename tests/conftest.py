@@ -37,6 +37,8 @@ def regenerate(meta):
     te = synth.synth_text_features(meta["n_test"], g["embed_dim"], meta["text_seeds"][1])
     task = synth.synth_episode(meta["way"], meta["shot"], 1, meta["T"], g["image_size"], meta["n_test"], meta["eseed"],
                                meta["structured"])
+    if meta.get("keep_counts"):
+        task = synth.ragged_support(task, meta["T"], meta["keep_counts"])
     return g, sd, tt, te, task
 
 

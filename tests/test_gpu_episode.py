@@ -58,7 +58,7 @@ def test_episode_matches_reference_fixture(lib, name):
     g, sd, tt, te, task = regenerate(meta)
     e = make_engine(lib, meta, g, sd, tt, te)
     logits, class_logits = run(e, meta, task)
-    S, Q, T, E, way = meta["way"] * meta["shot"], meta["way"], meta["T"], g["embed_dim"], meta["way"]
+    S, Q, T, E, way = len(task["support_labels"]), meta["way"], meta["T"], g["embed_dim"], meta["way"]
     tol_logits = 3e-3 if meta["spread"] else 1e-3
     mode = meta.get("text_mode", 0)
     slim = ref["support_feats"].size == 0
