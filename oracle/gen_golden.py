@@ -43,6 +43,8 @@ CASES = {
     # unequal shots per class: 3 / 1 / 2 support videos (class means over whatever members exist, few_shot.py:2949-2962)
     "tiny_ragged_3w": dict(geom="tiny", way=3, shot=3, T=8, keep_counts=[3, 1, 2]),
     "tiny_ragged_3w_merge": dict(geom="tiny", way=3, shot=3, T=8, keep_counts=[1, 3, 2], merge_before=True),
+    # several queries per class (QUERY_PER_CLASS_TEST > 1): 15 query videos against 5 prototypes
+    "tiny_5w1s_q3": dict(geom="tiny", way=5, shot=1, T=8, qpc=3),
     # text branches of the eval forward (few_shot.py:2835-2930)
     "tiny_5w5s_evaltext": dict(geom="tiny", way=5, shot=5, T=8, eval_text=True),
     "tiny_5w1s_combine": dict(geom="tiny", way=5, shot=1, T=8, combine=True),
@@ -110,7 +112,8 @@ def run_case(name, fs, BaseVideoModel, out_dir):
     sd = synth.synth_state_dict(g, seed=wseed, spread=case.get("spread", True))
     text_train = synth.synth_text_features(n_train, g["embed_dim"], seed=7)
     text_test = synth.synth_text_features(n_test, g["embed_dim"], seed=8)
-    task = synth.synth_episode(way, shot, 1, T, g["image_size"], n_test, seed=eseed, structured=case.get("structured", True))
+    task = synth.synth_episode(way, shot, case.get("qpc", 1), T, g["image_size"], n_test, seed=eseed,
+                               structured=case.get("structured", True))
     if case.get("keep_counts"):
         task = synth.ragged_support(task, T, case["keep_counts"])
 
@@ -145,7 +148,7 @@ def run_case(name, fs, BaseVideoModel, out_dir):
                 merge_before=bool(case.get("merge_before")), single_direct=bool(case.get("single_direct")),
                 mod_depth=case.get("mod_depth", 1), text_seeds=[7, 8],
                 text_mode=1 if case.get("eval_text") else (2 if case.get("combine") else 0),
-                text_coff=case.get("text_coff", 0.9), keep_counts=case.get("keep_counts"), reference_commit="30cf0a8c",
+                text_coff=case.get("text_coff", 0.9), keep_counts=case.get("keep_counts"), qpc=case.get("qpc", 1), reference_commit="30cf0a8c",
                 torch=torch.__version__, state_dict_keys=sorted(head.state_dict().keys()))
     no_ctx = len(taps["context2"]) == 0       # EVAL_TEXT never runs the modulator / OTAM
     arrays = dict(

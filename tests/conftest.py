@@ -35,7 +35,7 @@ def regenerate(meta):
     sd = synth.synth_state_dict(g, meta["wseed"], meta["spread"])
     tt = synth.synth_text_features(meta["n_train"], g["embed_dim"], meta["text_seeds"][0])
     te = synth.synth_text_features(meta["n_test"], g["embed_dim"], meta["text_seeds"][1])
-    task = synth.synth_episode(meta["way"], meta["shot"], 1, meta["T"], g["image_size"], meta["n_test"], meta["eseed"],
+    task = synth.synth_episode(meta["way"], meta["shot"], meta.get("qpc", 1), meta["T"], g["image_size"], meta["n_test"], meta["eseed"],
                                meta["structured"])
     if meta.get("keep_counts"):
         task = synth.ragged_support(task, meta["T"], meta["keep_counts"])

@@ -30,7 +30,7 @@ def rel_max(a, b):
 
 
 def make_engine(lib, meta, g, sd, tt, te, max_frames=None):
-    n_vid = meta["way"] * (meta["shot"] + 1)
+    n_vid = meta["way"] * (meta["shot"] + meta.get("qpc", 1))
     e = lib.Engine(**dict(g, max_frames=max_frames or n_vid * meta["T"], max_videos=n_vid, max_tokens=meta["T"],
                           max_classes=128, otam_lambda=0.5, device=0))
     ignored = e.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
@@ -58,7 +58,7 @@ def test_episode_matches_reference_fixture(lib, name):
     g, sd, tt, te, task = regenerate(meta)
     e = make_engine(lib, meta, g, sd, tt, te)
     logits, class_logits = run(e, meta, task)
-    S, Q, T, E, way = len(task["support_labels"]), meta["way"], meta["T"], g["embed_dim"], meta["way"]
+    S, Q, T, E, way = len(task["support_labels"]), len(task["target_labels"]), meta["T"], g["embed_dim"], meta["way"]
     tol_logits = 3e-3 if meta["spread"] else 1e-3
     mode = meta.get("text_mode", 0)
     slim = ref["support_feats"].size == 0
