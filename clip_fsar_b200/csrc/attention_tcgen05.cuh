@@ -28,9 +28,11 @@
 // beyond (ViT-L/14: 16 x 16 patches + CLS = 257) is folded in with scalar code:
 //   * extra key 256: every softmax thread adds s_x = q_row . k_256 (64 FMAs from smem) to its row max / row sum and
 //     p_x * v_256 to its O row before normalising;
-//   * extra query row 256: the otherwise idle warp 2 evaluates that single row against all 257 keys from the staged
-//     K / V tiles (lane = key for the scores, lane = two output columns for P V) and writes its 128 bytes itself.
-// That instance needs 2 x 99 KB of operand stages, so it writes O rows directly instead of staging them for TMA.
+//   * extra query row 256: four additional warps (12-15, one per SM sub-partition) evaluate that single row from the
+//     staged K / V tiles, 64 keys each (lane = key for the scores, lane = two output columns for P V), combine their
+//     max / sum / partial outputs through shared memory and write the row's 128 bytes.
+// That instance needs 2 x 99 KB of operand stages, so its softmax warps stage the O rows in their (by then dead) rows of
+// the Q tile and release the stage after the TMA store has read them.
 #pragma once
 #include "gemm_tcgen05.cuh"  // pack2<>
 #include "ptx.cuh"
@@ -50,7 +52,10 @@ struct Att5Cfg {
     static constexpr int STAGE_BYTES = ATT5_Q_BYTES + 2 * KV_BYTES + X_BYTES;
     static constexpr bool STAGED_OUT = (MAXK == 208);
     static constexpr int OUT_BYTES = STAGED_OUT ? 8 * ATT5_OUT_TILE_BYTES : 0;
-    static constexpr int SMEM_BYTES = 2 * STAGE_BYTES + OUT_BYTES + 256 + 1024;
+    static constexpr int X_WARPS = (MAXK == 256) ? 4 : 0;             // warps 12-15: the scalar query row, 64 keys each
+    static constexpr int THREADS = ATT5_THREADS + 32 * X_WARPS;
+    static constexpr int SCRATCH_BYTES = (MAXK == 256) ? 2048 : 0;    // reductions of the scalar-row warps
+    static constexpr int SMEM_BYTES = 2 * STAGE_BYTES + OUT_BYTES + SCRATCH_BYTES + 256 + 1024;
 };
 
 // 16-bit row `row` of a 128B-swizzled [rows][64] tile -> 64 floats (chunk c of row r sits at ((c ^ (r & 7)) << 4))
@@ -99,7 +104,7 @@ struct Att5Params {
 // CAUSAL: query token i attends to keys 0..i only (the additive -inf upper-triangular mask of the CLIP text transformer,
 // few_shot.py:777-783); the frame encoder uses CAUSAL = false.
 template <typename T16, bool CAUSAL, int MAXK>
-__global__ void __launch_bounds__(ATT5_THREADS, 1)
+__global__ void __launch_bounds__(Att5Cfg<MAXK>::THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                          const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmO,
                          const Att5Params p) {
@@ -112,7 +117,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_out = smem + 2 * ATT5_STAGE_BYTES;      // 8 softmax warps x [32 rows][128 B] (STAGED_OUT only)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + Cfg::OUT_BYTES);
+    float* x_scratch = reinterpret_cast<float*>(smem_out + Cfg::OUT_BYTES);   // [4] max | [4] sum | [4][64] partial O
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + Cfg::OUT_BYTES + Cfg::SCRATCH_BYTES);
     uint64_t* full_bar = bars;          // [2] TMA -> MMA
     uint64_t* empty_bar = bars + 2;     // [2] MMA -> TMA
     uint64_t* s_full = bars + 4;        // [2] per group: S ready
@@ -129,12 +135,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         tma_prefetch_desc(&tmQ);
         tma_prefetch_desc(&tmKV);
         if (kExtra) tma_prefetch_desc(&tmX);
-        if (Cfg::STAGED_OUT) tma_prefetch_desc(&tmO);
+        tma_prefetch_desc(&tmO);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], p.n_mtiles + (extra ? 1 : 0));   // one commit per row group (+ the scalar-row warp)
+            // a stage is refilled when every row group's P V has been committed (+ the scalar-row warp); the MAXK = 256
+            // instance also waits for the 4 softmax warps per group, which stage their output rows in the Q tile
+            mbar_init(&empty_bar[i], p.n_mtiles * (Cfg::STAGED_OUT ? 1 : 5) + (extra ? Cfg::X_WARPS : 0));
             mbar_init(&s_full[i], 1);
             mbar_init(&p_full[i], 4);
             mbar_init(&o_full[i], 1);
@@ -220,7 +228,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                 __syncwarp();
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 12) {
         // ------------------------------------------------------------ softmax + output: one thread per query row
         const int g = (warp - 4) >> 2;        // row group
         const int wq = warp & 3;              // TMEM lane quarter
@@ -229,8 +237,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             const bool warp_valid = (g * 128 + wq * 32) < p.Lm;
             const int n_keys = (CAUSAL && row + 1 < p.Lm) ? row + 1 : p.Lm;   // (tensor-core) keys of this query row
             const uint32_t t_row = tmem_base + g * 256 + (uint32_t(wq * 32) << 16);
-            const int n32 = p.LK / 32;             // full 32-column chunks of the score row
-            const bool tail16 = (p.LK & 16) != 0;  // plus one 16-column chunk
+            const int n32 = FSAR_PROBE(p.debug, 8) ? p.LK / 64 : p.LK / 32;   // full 32-column chunks of the score row
+            const bool tail16 = (p.LK & 16) != 0 && !FSAR_PROBE(p.debug, 8);  // plus one 16-column chunk
+            // (probe 8: every softmax thread handles half of its row = the per-thread work of a two-threads-per-row split)
             uint8_t* out_tile = smem_out + (warp - 4) * ATT5_OUT_TILE_BYTES;
             const uint32_t out_row = smem_u32(out_tile) + lane * 128;
             const uint32_t sw = uint32_t(lane & 7);     // 128B swizzle: 16-byte chunk index ^= row % 8
@@ -245,7 +254,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                 // scalar token 256 as a KEY: its score for this query row and its V row, straight from the staged tiles
                 // (they stay valid until this group's P V has been committed, i.e. until after the p_full arrival below)
                 float s_x = -INFINITY, p_x = 0.f;
-                uint4 vx[8];
                 if (extra && warp_valid) {
                     const uint8_t* stg = smem + (i & 1) * ATT5_STAGE_BYTES;
                     const uint8_t* q_tile = stg + g * 128 * 128;
@@ -259,7 +267,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                         const T16* ke = reinterpret_cast<const T16*>(&kb);
 #pragma unroll
                         for (int t = 0; t < 8; ++t) s_x = fmaf(float(qe[t]), float(ke[t]), s_x);
-                        vx[c] = *reinterpret_cast<const uint4*>(stg + X_OFF + 2048 + (c << 4));
                     }
                 }
                 if (warp_valid) {
@@ -364,11 +371,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&o_empty[g]);
-                if (extra && warp_valid) {   // O row += p_x * v_256
+                if (extra && warp_valid) {   // O row += p_x * v_256 (the stage is still ours: it is released below)
+                    const uint8_t* vx = smem + (i & 1) * ATT5_STAGE_BYTES + X_OFF + 2048;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const T16* v0 = reinterpret_cast<const T16*>(&vx[c]);
-                        const T16* v1 = reinterpret_cast<const T16*>(&vx[4 + c]);
+                        const uint4 va = *reinterpret_cast<const uint4*>(vx + (c << 4));
+                        const uint4 vb = *reinterpret_cast<const uint4*>(vx + ((4 + c) << 4));
+                        const T16* v0 = reinterpret_cast<const T16*>(&va);
+                        const T16* v1 = reinterpret_cast<const T16*>(&vb);
 #pragma unroll
                         for (int t = 0; t < 8; ++t) {
                             o0[8 * c + t] = __float_as_uint(fmaf(p_x, float(v0[t]), __uint_as_float(o0[8 * c + t])));
@@ -402,19 +412,39 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                             tma_store_3d(&tmO, out_tile, head * 64, g * 128 + wq * 32, frame);
                             tma_store_commit();
                         }
-                    } else if (row < p.L) {
-                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<T16*>(p.out) +
-                                                              ((size_t)frame * p.L + row) * p.D + head * 64);
+                    } else {
+                        // no room for separate staging tiles next to two 99 KB stages: this warp's 32 rows of the Q tile
+                        // (same 128B-swizzled [row][64] layout, dead since S = Q K^T completed) are the staging tile;
+                        // the stage is handed back to the producer only after the store has read them
+                        uint8_t* q_rows = smem + (i & 1) * ATT5_STAGE_BYTES + g * 128 * 128 + wq * ATT5_OUT_TILE_BYTES;
+                        const uint32_t q_row = smem_u32(q_rows) + lane * 128;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) dst[j] = v[j];
+                        for (int j = 0; j < 8; ++j)
+                            st_shared_v4(q_row + ((uint32_t(j) ^ sw) << 4), v[j].x, v[j].y, v[j].z, v[j].w);
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_3d(&tmO, q_rows, head * 64, g * 128 + wq * 32, frame);
+                            tma_store_commit();
+                            tma_store_wait_read<0>();
+                        }
                     }
                 }
+                if (!Cfg::STAGED_OUT) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty_bar[i & 1]);
+                }
             }
-            if (Cfg::STAGED_OUT && lane == 0) tma_store_wait<0>();   // output tiles are globally written before the CTA retires
+            if (lane == 0) tma_store_wait<0>();   // output tiles are globally written before the CTA retires
         }
-    } else if (warp == 2 && extra) {
-        // ------------------------------------------------------------ scalar token 256 as a QUERY row: one warp, all 257
-        // keys, from the staged tiles. Scores: lane = key (8 per lane); P V: lane = two output columns.
+    } else if (warp >= 12 && extra) {
+        // ------------------------------------------------------------ scalar token 256 as a QUERY row: warps 12-15, 64
+        // of the 256 staged keys each (warp 12 also takes key 256). Scores: lane = key (2 per lane); P V: lane = two
+        // output columns; row max, row sum and the partial O rows are combined through x_scratch.
+        const int xw = warp - 12;
+        float* x_max = x_scratch;          // [4]
+        float* x_sum = x_scratch + 4;      // [4]
+        float* x_part = x_scratch + 8;     // [4][64]
         T16* out = reinterpret_cast<T16*>(p.out);
         int i = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
@@ -426,38 +456,39 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             const uint8_t* k_tile = stg + ATT5_Q_BYTES;
             const uint8_t* v_tile = k_tile + ATT5_KV_BYTES;
             mbar_wait(&full_bar[s], ph);
+            if (FSAR_PROBE(p.debug, 16)) {   // probe: the scalar row costs nothing
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
+                continue;
+            }
             float q[64];
             att5_load_row<T16>(stg + X_OFF, 0, q);
-            float sc[8];
-            float mx = att5_dot_row<T16>(stg + X_OFF + 1024, 0, q);   // key 256
-            const float s_x = mx;
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                sc[t] = att5_dot_row<T16>(k_tile, lane + 32 * t, q);
-                mx = fmaxf(mx, sc[t]);
-            }
+            float sc[2];
+            sc[0] = att5_dot_row<T16>(k_tile, 64 * xw + lane, q);
+            sc[1] = att5_dot_row<T16>(k_tile, 64 * xw + 32 + lane, q);
+            const float s_x = (xw == 0) ? att5_dot_row<T16>(stg + X_OFF + 1024, 0, q) : -INFINITY;   // key 256
+            float mx = fmaxf(fmaxf(sc[0], sc[1]), s_x);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            const float m_scaled = mx * p.scale_log2e;
+            if (lane == 0) x_max[xw] = mx;
+            asm volatile("bar.sync 9, 128;" ::: "memory");
+            const float m_scaled = fmaxf(fmaxf(x_max[0], x_max[1]), fmaxf(x_max[2], x_max[3])) * p.scale_log2e;
             float sum = 0.f;
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
+            for (int t = 0; t < 2; ++t) {
                 const float e = ex2_approx(fmaf(sc[t], p.scale_log2e, -m_scaled));
                 sum += e;
-                sc[t] = float(T16(e));
+                sc[t] = float(T16(e));      // 16-bit like the P operand of the tensor-core rows
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            const float e_x = ex2_approx(fmaf(s_x, p.scale_log2e, -m_scaled));
-            sum += e_x;
-            const float p_x = float(T16(e_x));
             const uint32_t col = uint32_t(lane >> 2), sub = uint32_t(lane & 3) * 4;   // 16-byte chunk / byte offset inside it
             float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
+            for (int t = 0; t < 2; ++t) {
 #pragma unroll 8
                 for (int src = 0; src < 32; ++src) {
-                    const int j = 32 * t + src;
+                    const int j = 64 * xw + 32 * t + src;
                     const float pj = __shfl_sync(0xffffffffu, sc[t], src);
                     const uint32_t w = *reinterpret_cast<const uint32_t*>(v_tile + j * 128 + ((col ^ uint32_t(j & 7)) << 4) + sub);
                     const T16* e = reinterpret_cast<const T16*>(&w);
@@ -465,17 +496,29 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                     a1 = fmaf(pj, float(e[1]), a1);
                 }
             }
-            {
+            if (xw == 0) {
+                const float e_x = ex2_approx(fmaf(s_x, p.scale_log2e, -m_scaled));
+                sum += e_x;
+                const float p_x = float(T16(e_x));
                 const uint32_t w = *reinterpret_cast<const uint32_t*>(stg + X_OFF + 2048 + (col << 4) + sub);
                 const T16* e = reinterpret_cast<const T16*>(&w);
                 a0 = fmaf(p_x, float(e[0]), a0);
                 a1 = fmaf(p_x, float(e[1]), a1);
             }
-            const float inv = 1.0f / sum;
-            *reinterpret_cast<uint32_t*>(out + ((size_t)frame * p.L + 256) * p.D + head * 64 + 2 * lane) =
-                pack2<T16>(a0 * inv, a1 * inv);
+            x_part[xw * 64 + 2 * lane] = a0;
+            x_part[xw * 64 + 2 * lane + 1] = a1;
+            if (lane == 0) x_sum[xw] = sum;
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);   // this warp no longer reads the stage
+            asm volatile("bar.sync 9, 128;" ::: "memory");
+            if (xw == 0) {
+                const float inv = 1.0f / ((x_sum[0] + x_sum[1]) + (x_sum[2] + x_sum[3]));
+                const float o0 = (x_part[2 * lane] + x_part[64 + 2 * lane]) + (x_part[128 + 2 * lane] + x_part[192 + 2 * lane]);
+                const float o1 = (x_part[2 * lane + 1] + x_part[64 + 2 * lane + 1]) +
+                                 (x_part[128 + 2 * lane + 1] + x_part[192 + 2 * lane + 1]);
+                *reinterpret_cast<uint32_t*>(out + ((size_t)frame * p.L + 256) * p.D + head * 64 + 2 * lane) =
+                    pack2<T16>(o0 * inv, o1 * inv);
+            }
         }
     }
 

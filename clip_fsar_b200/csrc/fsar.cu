@@ -421,7 +421,7 @@ int attention(fsar_handle* h, const T16* qkv, int n_frames, int L, int heads, T1
         if (causal)
             launch_pdl(h, attention_tcgen05_kernel<T16, true, 208>, dim3(grid5), dim3(ATT5_THREADS), Att5Cfg<208>::SMEM_BYTES, st, tq, tkv, tx, to, ap);
         else if (big)
-            launch_pdl(h, attention_tcgen05_kernel<T16, false, 256>, dim3(grid5), dim3(ATT5_THREADS), Att5Cfg<256>::SMEM_BYTES, st, tq, tkv, tx, to, ap);
+            launch_pdl(h, attention_tcgen05_kernel<T16, false, 256>, dim3(grid5), dim3(Att5Cfg<256>::THREADS), Att5Cfg<256>::SMEM_BYTES, st, tq, tkv, tx, to, ap);
         else
             launch_pdl(h, attention_tcgen05_kernel<T16, false, 208>, dim3(grid5), dim3(ATT5_THREADS), Att5Cfg<208>::SMEM_BYTES, st, tq, tkv, tx, to, ap);
         return check_launch(h, "attention_tcgen05_kernel");

@@ -73,7 +73,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("FSAR_LIB_PATH") or LIB_PATH     # the environment is read at load time, not import time
     if not os.path.exists(p):
         raise FileNotFoundError(
             "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -4,8 +4,8 @@ import json, os, subprocess, sys, time
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from clip_fsar_b200 import build as B
-os.environ.setdefault("FSAR_LIB_PATH", B.OUT_PROBES)      # the -DFSAR_PROBES build honours FSAR_GEMM_DEBUG / FSAR_ATT_DEBUG
+# the -DFSAR_PROBES build (python clip_fsar_b200/build.py --probes) honours FSAR_GEMM_DEBUG / FSAR_ATT_DEBUG
+os.environ.setdefault("FSAR_LIB_PATH", os.path.join(ROOT, "clip_fsar_b200", "libfsar_sm100_probes.so"))
 from clip_fsar_b200 import lib as L, synth
 
 def sample_start():
@@ -38,9 +38,11 @@ def run(name, fn, flops, secs=1.0):
 g = synth.full_geometry("tiny")
 eng = L.Engine(**dict(g, max_frames=16, max_videos=10, max_tokens=8, max_classes=64, otam_lambda=0.5, device=0))
 dt = eng.operand_dtype; DEV = "cuda:0"; M = int(os.environ.get("PROBE_M", 96 * 197))
-for (N, K, epi, nm) in ((2304, 768, L.EPI_STORE16, "qkv"), (768, 768, L.EPI_RESID32, "out"), (3072, 768, L.EPI_QGELU16, "fc1"), (768, 3072, L.EPI_RESID32, "fc2")):
+for (N, K, epi, nm) in () if os.environ.get("PROBE_ONLY") == "att" else ((2304, 768, L.EPI_STORE16, "qkv"), (768, 768, L.EPI_RESID32, "out"), (3072, 768, L.EPI_QGELU16, "fc1"), (768, 3072, L.EPI_RESID32, "fc2")):
     a = (torch.randn(M, K, device=DEV) * 0.1).to(dt); w = (torch.randn(N, K, device=DEV) * 0.1).to(dt); b = torch.randn(N, device=DEV)
     out = torch.zeros(M, N, device=DEV, dtype=dt if epi in (0, 1) else torch.float32)
     run("gemm_" + nm, lambda: eng.op_gemm(a, w, b, epi, out=out), 2.0 * M * N * K)
 qkv = torch.randn(M, 2304, device=DEV).to(dt)
 run("attention", lambda: eng.op_attention(qkv, M // 197, 197, 12), 4.0 * (M // 197) * 12 * 197 * 197 * 64)
+qkv = torch.randn(96 * 257, 3 * 1024, device=DEV).to(dt)
+run("attention_l14", lambda: eng.op_attention(qkv, 96, 257, 16), 4.0 * 96 * 16 * 257 * 257 * 64)
