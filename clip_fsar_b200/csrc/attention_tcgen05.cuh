@@ -98,7 +98,7 @@ struct Att5Params {
     void* out;       // [n_frames * L, D] 16-bit (written through tmO)
     int reverse;     // walk the (frame, head) items last-to-first (L2 reuse of the QKV rows written last)
     int debug;       // only read by the -DFSAR_PROBES build (tools/gemm_probe.py, results WRONG): 1 skip the max pass,
-                     // 2 no exp2, 4 no stores
+                     // 2 no exp2, 4 no stores, 8 softmax threads process half of their row, 16 no scalar query row
 };
 
 // CAUSAL: query token i attends to keys 0..i only (the additive -inf upper-triangular mask of the CLIP text transformer,
