@@ -212,6 +212,9 @@ TEXT_CASES = {
                                "air drumming", "blasting sand", "busking", "cutting watermelon", "dancing ballet",
                                "diving cliff", "filling eyebrows", "folding paper", "hula hooping", "ice skating",
                                "paragliding", "playing trumpet", "shearing sheep", "unboxing"]),
+    # the ViT-L/14 text tower: width 768, 12 heads, 12 layers, embed 768
+    "text_vitl14": dict(geom="ViT-L/14", embed_dim=768, prompt="a photo of {}",
+                        names=["brush hair", "cartwheel", "catch", "chew", "climb stairs", "fencing"]),
     "text_tiny_prompt": dict(geom="tiny", embed_dim=128, prompt="a video of a person {}, a type of action",
                              names=["stretching arm", "throwing axe", "side kick"]),
 }

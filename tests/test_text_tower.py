@@ -9,7 +9,7 @@ from conftest import load_golden
 from clip_fsar_b200 import synth
 from oracle import fsar_oracle as O
 
-CASES = ["text_tiny", "text_tiny_prompt", "text_vitb16"]
+CASES = ["text_tiny", "text_tiny_prompt", "text_vitb16", "text_vitl14"]
 
 
 def regenerate_text(meta):
@@ -49,10 +49,9 @@ def test_oracle_text_mask_is_causal():
 def test_gpu_text_encode_matches_reference(lib, name):
     meta, ref = load_golden(name)
     tg, sd = regenerate_text(meta)
-    vis = "ViT-B/16" if meta["geom"] == "ViT-B/16" else meta["geom"]
-    g = synth.full_geometry(vis)
+    g = synth.full_geometry("l14-2layer" if meta["geom"] == "ViT-L/14" else meta["geom"])   # only embed_dim matters here
     assert g["embed_dim"] == meta["embed_dim"]
-    eng = lib.Engine(**dict(g, max_frames=8 if meta["geom"] == "ViT-B/16" else 80, max_videos=10, max_tokens=8, max_classes=64,
+    eng = lib.Engine(**dict(g, max_frames=8 if meta["geom"] in ("ViT-B/16", "ViT-L/14") else 80, max_videos=10, max_tokens=8, max_classes=64,
                             otam_lambda=0.5, device=0))
     try:
         with pytest.raises(lib.FsarError):              # not configured yet
