@@ -127,6 +127,7 @@ struct fsar_handle {
     bool alternate_rows = true;     // FSAR_NO_ALTERNATE=1: every kernel walks rows first-to-last (A/B testing)
     bool single_cta_gemm = false;   // FSAR_GEMM_SINGLE=1: one CTA per 128 x 256 tile instead of CTA pairs (A/B testing)
     int gemm_debug = 0;             // FSAR_GEMM_DEBUG: bottleneck probes, -DFSAR_PROBES build only (tools/gemm_probe.py)
+    int small_m = 128;              // FSAR_SMALL_M: GEMMs with at most this many rows use 64-column single-CTA tiles
     bool cls_last_block = true;     // FSAR_FULL_LAST_BLOCK=1: the last block also computes the token rows nobody reads
     bool pdl = true;                // FSAR_NO_PDL=1: no programmatic dependent launch between the frame-encoder kernels
     bool legacy_attention = false;  // FSAR_LEGACY_ATTENTION=1: mma.sync attention core also for L <= 208 (A/B testing)
@@ -335,7 +336,9 @@ int gemm(fsar_handle* h, int cls, const T16* a, const T16* w, const float* bias,
         return fail(h, FSAR_E_INVALID, "gemm: operands must be 16-byte aligned");
     GemmParams p{};
     p.M = M; p.N = N; p.K = K; p.bias = bias; p.reverse = reverse; p.debug = h->gemm_debug;
-    const int bn = (N >= 256) ? 256 : ((N >= 128) ? 128 : 64);
+    // a handful of rows (the CLS rows of the last block): 64-column tiles on single CTAs, so that N / 64 SMs pull the
+    // weights instead of N / 256 CTA pairs -- these launches are bound by what one SM can ingest
+    const int bn = (M <= h->small_m) ? 64 : ((N >= 256) ? 256 : ((N >= 128) ? 128 : 64));
     const bool out16 = (epi == EPI_STORE16 || epi == EPI_QGELU16);
     CUtensorMap ta, tb, tc;
     const bool pair = (bn == 256) && !h->single_cta_gemm;   // CTA pairs (cta_group::2, 256 x 256 tiles)
@@ -984,6 +987,8 @@ int fsar_create(const fsar_config* cfg, fsar_handle** out) {
         h->single_cta_gemm = (e != nullptr && e[0] == '1');
         e = getenv("FSAR_GEMM_DEBUG");
         h->gemm_debug = e != nullptr ? atoi(e) : 0;
+        e = getenv("FSAR_SMALL_M");
+        if (e != nullptr) h->small_m = atoi(e);
         e = getenv("FSAR_FULL_LAST_BLOCK");
         h->cls_last_block = !(e != nullptr && e[0] == '1');
         e = getenv("FSAR_NO_PDL");
