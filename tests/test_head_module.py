@@ -106,3 +106,38 @@ def test_synthetic_dataset_matches_reference_task_dict():
     assert item["support_set"].shape == (40, 3, 32, 32) and item["support_set"].dtype == torch.float32
     assert sorted(item["support_labels"].tolist()) == [0.0, 1.0, 2.0, 3.0, 4.0]
     assert torch.equal(ds[1]["target_set"], item["target_set"])        # seeded by index
+
+
+def test_clip_checkpoint_fills_backbone_and_schedules_text_tower(tmp_path):
+    """VIDEO.HEAD.CLIP_CHECKPOINT: 'visual.*' -> backbone.*, the rest -> the library's text tower at the first forward
+    (few_shot.py:2706-2728 does load(...) + encode_text in the constructor)."""
+    from clip_fsar_b200 import synth
+    from clip_fsar_b200.head import CNN_OTAM_CLIPFSAR_SM100
+    g = synth.full_geometry("tiny")
+    vis = {k[len("backbone."):]: torch.from_numpy(v) for k, v in synth.synth_state_dict(g, 5).items() if k.startswith("backbone.")}
+    tg = synth.TEXT_GEOMETRIES["tiny"]
+    txt = {k: torch.from_numpy(v) for k, v in synth.synth_text_state_dict(tg, g["embed_dim"], 3).items()}
+    ckpt = {("visual." + k): v for k, v in vis.items()}
+    ckpt.update(txt)
+    ckpt["logit_scale"] = torch.tensor(4.6)
+    path = os.path.join(tmp_path, "clip_tiny.pt")
+    torch.save(ckpt, path)
+    cfg = make_cfg(backbone="tiny")
+    cfg.VIDEO.HEAD.SYNTHETIC_TEXT = False
+    cfg.VIDEO.HEAD.CLIP_CHECKPOINT = path
+    cfg.TEST.PROMPT = "a video of {}"
+    prompts = []
+
+    def tokenizer(ps):
+        prompts.append(list(ps))
+        return torch.zeros(len(ps), 77, dtype=torch.int32)
+
+    head = CNN_OTAM_CLIPFSAR_SM100(cfg, tokenizer=tokenizer)
+    assert torch.equal(head.backbone.proj, vis["proj"])
+    assert torch.equal(head.backbone.transformer.resblocks[1].mlp.c_fc.weight, vis["transformer.resblocks.1.mlp.c_fc.weight"])
+    assert head._text_pending and head._text_geometry == tg
+    assert prompts[0][0] == "a video of c0" and prompts[1][0] == "a video of t0" and len(prompts[1]) == 24
+    assert "logit_scale" not in head._text_state and "token_embedding.weight" in head._text_state
+    # explicit features cancel the pending text-tower run
+    head.set_text_features(torch.zeros(64, g["embed_dim"]), torch.zeros(24, g["embed_dim"]))
+    assert not head._text_pending
