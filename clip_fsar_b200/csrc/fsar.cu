@@ -27,6 +27,9 @@
 #include "head_kernels.cuh"
 #include "text_kernels.cuh"
 #include "vit_kernels.cuh"
+#ifdef FSAR_PROBES
+#include "probes_attention_mma.cuh"   // round-1 mma.sync attention, A/B baseline of tools/gemm_probe.py only
+#endif
 
 using namespace fsar;
 
@@ -63,6 +66,23 @@ struct HeadWs {
     int *cls = nullptr, *counts = nullptr;
 };
 
+// Device pointers of the weights, resolved once (fsar_create / fsar_text_configure): the allocations never move, so the
+// launch sequence does no string building or map lookups (~90 per ViT pass before).
+struct BlockW {   // one ResidualAttentionBlock (few_shot.py:619-640), frame encoder or text tower
+    const T16 *w_in, *w_out, *w_fc, *w_proj;
+    const float *b_in, *b_out, *b_fc, *b_proj, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+};
+struct ModW {     // one Transformer_v1 layer (few_shot.py:979-999)
+    const float *norm_g, *norm_b, *qkv, *w_out, *b_out, *w_fc, *b_fc, *w_proj, *b_proj;
+};
+struct VitW {
+    const T16* conv1;
+    const float *cls_emb, *pos, *ln_pre_g, *ln_pre_b, *ln_post_g, *ln_post_b, *proj, *scale, *text_train, *text_test;
+};
+struct TextW {
+    const float *tok, *pos, *lnf_g, *lnf_b, *proj;
+};
+
 struct ProfRec {
     int cls;
     cudaEvent_t a, b;
@@ -96,6 +116,11 @@ struct fsar_handle {
     fsar_text_config text_cfg = {0, 0, 0, 0, 0};   // width == 0: no text tower configured
     // fused modulator QKV weights: one [3 * inner, E] allocation per layer
     std::vector<float*> mod_qkv;
+    // resolved device pointers (see BlockW)
+    VitW vw{};
+    TextW tw{};
+    std::vector<BlockW> vit_blocks, text_blocks;
+    std::vector<ModW> mod_layers;
     // ---- ViT workspace (capacity cfg.max_frames)
     T16 *patches16 = nullptr, *ln16 = nullptr, *qkv16 = nullptr, *att16 = nullptr, *h16 = nullptr;
     T16 *cls_q16 = nullptr, *cls_att16 = nullptr, *cls_ln16 = nullptr, *cls_h16 = nullptr;   // last block: CLS rows only
@@ -120,17 +145,28 @@ struct fsar_handle {
     // ---- host-buffer path
     HostSlot slot[2];
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+    // ---- device-side input validation: kernels that index text_features_test with caller labels clamp
+    // the index and raise bits of this flag, which lives in mapped pinned host memory: the host reads it without a
+    // synchronisation of its own -- exactly after the event wait in *_collect_host, lazily (at the next call) on the
+    // stream-ordered device entry points.
+    int* status_host = nullptr;   // [0]: real_support_labels outside [0, n_text_test); [1]: more distinct support_labels
+    int* status_dev = nullptr;    //      than `way`
     // ---- instrumentation
     int64_t launches = 0;
     bool profiling = false;
     size_t l2_persist_bytes = 0, l2_window_max = 0;   // L2 set-aside for the residual stream (0 = disabled)
-    bool alternate_rows = true;     // FSAR_NO_ALTERNATE=1: every kernel walks rows first-to-last (A/B testing)
-    bool single_cta_gemm = false;   // FSAR_GEMM_SINGLE=1: one CTA per 128 x 256 tile instead of CTA pairs (A/B testing)
-    int gemm_debug = 0;             // FSAR_GEMM_DEBUG: bottleneck probes, -DFSAR_PROBES build only (tools/gemm_probe.py)
-    int small_m = 128;              // FSAR_SMALL_M: GEMMs with at most this many rows use 64-column single-CTA tiles
+    // Verification knobs of the product library (read once at fsar_create):
     bool cls_last_block = true;     // FSAR_FULL_LAST_BLOCK=1: the last block also computes the token rows nobody reads
+                                    // (tests/test_gpu_episode.py proves both give the same frame features)
     bool pdl = true;                // FSAR_NO_PDL=1: no programmatic dependent launch between the frame-encoder kernels
-    bool legacy_attention = false;  // FSAR_LEGACY_ATTENTION=1: mma.sync attention core also for L <= 208 (A/B testing)
+    // A/B switches that only exist in the -DFSAR_PROBES build (libfsar_sm100_probes.so, tools/gemm_probe.py); in the
+    // product library they are compile-time constants and the alternative code paths are not compiled in:
+    bool alternate_rows = true;     // FSAR_NO_ALTERNATE=1: every kernel walks rows first-to-last
+    bool single_cta_gemm = false;   // FSAR_GEMM_SINGLE=1: one CTA per 128 x 256 tile instead of CTA pairs
+    int gemm_debug = 0;             // FSAR_GEMM_DEBUG: bottleneck probes (results are WRONG when set)
+    int att_debug = 0;              // FSAR_ATT_DEBUG: same for the attention core
+    int small_m = 128;              // FSAR_SMALL_M: GEMMs with at most this many rows use 64-column single-CTA tiles
+    bool legacy_attention = false;  // FSAR_LEGACY_ATTENTION=1: round-1 mma.sync attention core
     std::vector<ProfRec> prof;
 };
 
@@ -145,6 +181,16 @@ int fail(fsar_handle* h, int code, const char* fmt, ...) {
     if (h) h->err = buf; else g_create_error = buf;
     return code;
 }
+
+// Every entry point runs on the handle's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    explicit DeviceGuard(const fsar_handle* h);
+    ~DeviceGuard() {
+        if (changed) cudaSetDevice(prev);
+    }
+};
 
 #define CU_OK(h, expr)                                                                                    \
     do {                                                                                                  \
@@ -161,6 +207,25 @@ int fail(fsar_handle* h, int code, const char* fmt, ...) {
     } while (0)
 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+DeviceGuard::DeviceGuard(const fsar_handle* h) {
+    if (h == nullptr) return;
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != h->cfg.device) changed = (cudaSetDevice(h->cfg.device) == cudaSuccess);
+}
+
+// Report (and clear) what the label-checking kernels of EARLIER episodes flagged.
+int check_status(fsar_handle* h) {
+    if (h->status_host == nullptr) return 0;
+    volatile int* f = reinterpret_cast<volatile int*>(h->status_host);
+    const int st = (f[0] ? 1 : 0) | (f[1] ? 2 : 0);
+    if (st == 0) return 0;
+    f[0] = 0;
+    f[1] = 0;
+    if (st & 1)
+        return fail(h, FSAR_E_INVALID, "an episode carried real_support_labels outside [0, %d) (rows of text_features_test); "
+                    "its logits are invalid (the reference raises IndexError at few_shot.py:2946)", h->n_text_test);
+    return fail(h, FSAR_E_INVALID, "an episode carried more distinct support_labels than its `way`; its logits are invalid");
+}
 
 // ---------------------------------------------------------------- profiling helpers
 struct Scope {
@@ -347,7 +412,9 @@ int gemm(fsar_handle* h, int cls, const T16* a, const T16* w, const float* bias,
     RET_IF(get_tmap(h, out, M, N, 32, out16 ? 64 : 32, out16 ? 0 : 1, &tc, ldc));
     Scope s(h, st, cls, 2.0 * M * N * K, 0.0);
     if (pair) return launch_gemm_pair(h, epi, ta, tb, tc, p, st);
-    if (bn == 256) return launch_gemm_bn<256>(h, epi, ta, tb, tc, p, st);
+#ifdef FSAR_PROBES
+    if (bn == 256) return launch_gemm_bn<256>(h, epi, ta, tb, tc, p, st);   // FSAR_GEMM_SINGLE=1 A/B only
+#endif
     if (bn == 128) return launch_gemm_bn<128>(h, epi, ta, tb, tc, p, st);
     return launch_gemm_bn<64>(h, epi, ta, tb, tc, p, st);
 }
@@ -401,45 +468,48 @@ int attention(fsar_handle* h, const T16* qkv, int n_frames, int L, int heads, T1
             (double)n_frames * L * D * 2.0 * 4.0);
     if (causal && L > ATT5_MAX_KEYS)
         return fail(h, FSAR_E_INVALID, "causal attention supports at most %d tokens, got %d", ATT5_MAX_KEYS, L);
-    if (L <= ATT5_MAX_TOKENS && (!h->legacy_attention || causal)) {
-        // tcgen05 / TMEM path: S and O accumulate in tensor memory, one softmax thread per query row.
-        // L <= 208: MAXK = 208 instance (TMA-staged output); 208 < L <= 257: MAXK = 256 instance (ViT-L/14: 256 tokens
-        // on the tensor cores + one scalar token).
-        const bool big = L > ATT5_MAX_KEYS;
-        RET_IF(ensure_smem(h, attention_tcgen05_kernel<T16, false, 208>, Att5Cfg<208>::SMEM_BYTES));
-        RET_IF(ensure_smem(h, attention_tcgen05_kernel<T16, true, 208>, Att5Cfg<208>::SMEM_BYTES));
-        RET_IF(ensure_smem(h, attention_tcgen05_kernel<T16, false, 256>, Att5Cfg<256>::SMEM_BYTES));
-        Att5Params ap{};
-        ap.n_frames = n_frames; ap.L = L; ap.heads = heads; ap.D = D;
-        ap.Lm = L < 256 ? L : 256; ap.extra = L - ap.Lm;
-        ap.LK = round_up(ap.Lm, 16); ap.n_mtiles = (ap.Lm + 127) / 128; ap.scale_log2e = scale_log2e; ap.out = out; ap.reverse = reverse;
-        { const char* e = getenv("FSAR_ATT_DEBUG"); ap.debug = e ? atoi(e) : 0; }
-        CUtensorMap tq, tkv, tx, to;
-        RET_IF(get_tmap(h, qkv, n_frames * L, 3 * D, 128, 64, 0, &tq));
-        RET_IF(get_tmap(h, qkv, n_frames * L, 3 * D, ap.LK, 64, 0, &tkv));
-        RET_IF(get_tmap(h, qkv, n_frames * L, 3 * D, 8, 64, 0, &tx));
-        RET_IF(get_tmap_tokens3d(h, out, n_frames, L, D, &to));
-        const int items = n_frames * heads;
-        const int grid5 = items < h->sms ? items : h->sms;
-        if (causal)
-            launch_pdl(h, attention_tcgen05_kernel<T16, true, 208>, dim3(grid5), dim3(ATT5_THREADS), Att5Cfg<208>::SMEM_BYTES, st, tq, tkv, tx, to, ap);
-        else if (big)
-            launch_pdl(h, attention_tcgen05_kernel<T16, false, 256>, dim3(grid5), dim3(Att5Cfg<256>::THREADS), Att5Cfg<256>::SMEM_BYTES, st, tq, tkv, tx, to, ap);
-        else
-            launch_pdl(h, attention_tcgen05_kernel<T16, false, 208>, dim3(grid5), dim3(ATT5_THREADS), Att5Cfg<208>::SMEM_BYTES, st, tq, tkv, tx, to, ap);
-        return check_launch(h, "attention_tcgen05_kernel");
+#ifdef FSAR_PROBES
+    if (h->legacy_attention && !causal && L <= 272) {
+        const dim3 grid((L + ATT_QROWS - 1) / ATT_QROWS, heads, n_frames);
+        if (L <= 208) {
+            RET_IF(ensure_smem(h, attention_mma_kernel<T16, 13>, att_smem_bytes<13>()));
+            launch_pdl(h, attention_mma_kernel<T16, 13>, grid, dim3(128), att_smem_bytes<13>(), st, qkv, out, L, D, scale_log2e);
+        } else {
+            RET_IF(ensure_smem(h, attention_mma_kernel<T16, 17>, att_smem_bytes<17>()));
+            launch_pdl(h, attention_mma_kernel<T16, 17>, grid, dim3(128), att_smem_bytes<17>(), st, qkv, out, L, D, scale_log2e);
+        }
+        return check_launch(h, "attention_mma_kernel");
     }
-    const dim3 grid((L + ATT_QROWS - 1) / ATT_QROWS, heads, n_frames);
-    if (L <= 208) {
-        RET_IF(ensure_smem(h, attention_mma_kernel<T16, 13>, att_smem_bytes<13>()));
-        launch_pdl(h, attention_mma_kernel<T16, 13>, grid, dim3(128), att_smem_bytes<13>(), st, qkv, out, L, D, scale_log2e);
-    } else if (L <= 272) {
-        RET_IF(ensure_smem(h, attention_mma_kernel<T16, 17>, att_smem_bytes<17>()));
-        launch_pdl(h, attention_mma_kernel<T16, 17>, grid, dim3(128), att_smem_bytes<17>(), st, qkv, out, L, D, scale_log2e);
-    } else {
-        return fail(h, FSAR_E_INVALID, "attention: %d tokens per frame exceeds the supported 272", L);
-    }
-    return check_launch(h, "attention_mma_kernel");
+#endif
+    if (L > ATT5_MAX_TOKENS)
+        return fail(h, FSAR_E_INVALID, "attention: %d tokens per frame exceeds the supported %d (ViT-L/14 at 224 x 224)", L,
+                    ATT5_MAX_TOKENS);
+    // tcgen05 / TMEM path: S and O accumulate in tensor memory, one softmax thread per query row.
+    // L <= 208: MAXK = 208 instance (TMA-staged output); 208 < L <= 257: MAXK = 256 instance (ViT-L/14: 256 tokens
+    // on the tensor cores + one scalar token).
+    const bool big = L > ATT5_MAX_KEYS;
+    RET_IF(ensure_smem(h, attention_tcgen05_kernel<T16, false, 208>, Att5Cfg<208>::SMEM_BYTES));
+    RET_IF(ensure_smem(h, attention_tcgen05_kernel<T16, true, 208>, Att5Cfg<208>::SMEM_BYTES));
+    RET_IF(ensure_smem(h, attention_tcgen05_kernel<T16, false, 256>, Att5Cfg<256>::SMEM_BYTES));
+    Att5Params ap{};
+    ap.n_frames = n_frames; ap.L = L; ap.heads = heads; ap.D = D;
+    ap.Lm = L < 256 ? L : 256; ap.extra = L - ap.Lm;
+    ap.LK = round_up(ap.Lm, 16); ap.n_mtiles = (ap.Lm + 127) / 128; ap.scale_log2e = scale_log2e; ap.out = out; ap.reverse = reverse;
+    ap.debug = h->att_debug;
+    CUtensorMap tq, tkv, tx, to;
+    RET_IF(get_tmap(h, qkv, n_frames * L, 3 * D, 128, 64, 0, &tq));
+    RET_IF(get_tmap(h, qkv, n_frames * L, 3 * D, ap.LK, 64, 0, &tkv));
+    RET_IF(get_tmap(h, qkv, n_frames * L, 3 * D, 8, 64, 0, &tx));
+    RET_IF(get_tmap_tokens3d(h, out, n_frames, L, D, &to));
+    const int items = n_frames * heads;
+    const int grid5 = items < h->sms ? items : h->sms;
+    if (causal)
+        launch_pdl(h, attention_tcgen05_kernel<T16, true, 208>, dim3(grid5), dim3(ATT5_THREADS), Att5Cfg<208>::SMEM_BYTES, st, tq, tkv, tx, to, ap);
+    else if (big)
+        launch_pdl(h, attention_tcgen05_kernel<T16, false, 256>, dim3(grid5), dim3(Att5Cfg<256>::THREADS), Att5Cfg<256>::SMEM_BYTES, st, tq, tkv, tx, to, ap);
+    else
+        launch_pdl(h, attention_tcgen05_kernel<T16, false, 208>, dim3(grid5), dim3(ATT5_THREADS), Att5Cfg<208>::SMEM_BYTES, st, tq, tkv, tx, to, ap);
+    return check_launch(h, "attention_tcgen05_kernel");
 }
 
 template <int ACT>
@@ -469,6 +539,7 @@ void add_w(fsar_handle* h, const std::string& name, int64_t numel, int rows = 0,
 }
 
 int alloc_weight_storage(fsar_handle* h);
+void resolve_weights(fsar_handle* h);
 
 int alloc_weights(fsar_handle* h) {
     const fsar_config& c = h->cfg;
@@ -518,7 +589,9 @@ int alloc_weights(fsar_handle* h) {
     h->mod_qkv.assign(c.mod_depth, nullptr);
     for (int l = 0; l < c.mod_depth; ++l)
         CU_OK(h, cudaMalloc(&h->mod_qkv[l], sizeof(float) * 3 * (size_t)inner * E));
-    return alloc_weight_storage(h);
+    RET_IF(alloc_weight_storage(h));
+    resolve_weights(h);
+    return 0;
 }
 
 int alloc_weight_storage(fsar_handle* h) {
@@ -542,6 +615,45 @@ int alloc_weight_storage(fsar_handle* h) {
         if (w.rows > 0) CU_OK(h, cudaMalloc(&w.d16, sizeof(T16) * (size_t)w.rows * w.kp));
     }
     return 0;
+}
+
+void resolve_blocks(fsar_handle* h, const std::string& root, int layers, std::vector<BlockW>* out) {
+    out->resize(layers);
+    for (int i = 0; i < layers; ++i) {
+        const std::string p = root + "transformer.resblocks." + std::to_string(i) + ".";
+        BlockW& b = (*out)[i];
+        b.w_in = W16(h, p + "attn.in_proj_weight");   b.b_in = W32(h, p + "attn.in_proj_bias");
+        b.w_out = W16(h, p + "attn.out_proj.weight"); b.b_out = W32(h, p + "attn.out_proj.bias");
+        b.w_fc = W16(h, p + "mlp.c_fc.weight");       b.b_fc = W32(h, p + "mlp.c_fc.bias");
+        b.w_proj = W16(h, p + "mlp.c_proj.weight");   b.b_proj = W32(h, p + "mlp.c_proj.bias");
+        b.ln1_g = W32(h, p + "ln_1.weight"); b.ln1_b = W32(h, p + "ln_1.bias");
+        b.ln2_g = W32(h, p + "ln_2.weight"); b.ln2_b = W32(h, p + "ln_2.bias");
+    }
+}
+
+void resolve_weights(fsar_handle* h) {
+    const fsar_config& c = h->cfg;
+    VitW& v = h->vw;
+    v.conv1 = W16(h, "backbone.conv1.weight");
+    v.cls_emb = W32(h, "backbone.class_embedding");
+    v.pos = W32(h, "backbone.positional_embedding");
+    v.ln_pre_g = W32(h, "backbone.ln_pre.weight");   v.ln_pre_b = W32(h, "backbone.ln_pre.bias");
+    v.ln_post_g = W32(h, "backbone.ln_post.weight"); v.ln_post_b = W32(h, "backbone.ln_post.bias");
+    v.proj = W32(h, "backbone.proj");
+    v.scale = W32(h, "scale");
+    v.text_train = W32(h, "text_features_train");
+    v.text_test = W32(h, "text_features_test");
+    resolve_blocks(h, "backbone.", c.layers, &h->vit_blocks);
+    h->mod_layers.resize(c.mod_depth);
+    for (int l = 0; l < c.mod_depth; ++l) {
+        const std::string p = "context2.layers." + std::to_string(l) + ".";
+        ModW& m = h->mod_layers[l];
+        m.norm_g = W32(h, p + "0.norm.weight"); m.norm_b = W32(h, p + "0.norm.bias");
+        m.qkv = h->mod_qkv[l];
+        m.w_out = W32(h, p + "0.fn.to_out.0.weight"); m.b_out = W32(h, p + "0.fn.to_out.0.bias");
+        m.w_fc = W32(h, p + "1.net.0.weight");        m.b_fc = W32(h, p + "1.net.0.bias");
+        m.w_proj = W32(h, p + "1.net.3.weight");      m.b_proj = W32(h, p + "1.net.3.bias");
+    }
 }
 
 template <typename T>
@@ -632,11 +744,11 @@ int vit_encode_gathered(fsar_handle* h, int n, float* feats_out, cudaStream_t st
     set_l2_window(h, st, h->x32, sizeof(float) * (size_t)M * D);
     // conv1 as a GEMM into a scratch [n * G * G, D] fp32 (the MLP hidden buffer is free at this point) ...
     float* patch32 = reinterpret_cast<float*>(h->h16);
-    RET_IF(gemm(h, FSAR_K_GEMM_PATCH, h->patches16, W16(h, "backbone.conv1.weight"), nullptr, patch32, n * G2, D,
+    RET_IF(gemm(h, FSAR_K_GEMM_PATCH, h->patches16, h->vw.conv1, nullptr, patch32, n * G2, D,
                 h->patch_kp, EPI_STORE32, st));
     // ... and ln_pre assembles [CLS | patches] + positional embedding on the fly (few_shot.py:675-677)
-    RET_IF(layernorm(h, patch32, h->x32, W32(h, "backbone.ln_pre.weight"), W32(h, "backbone.ln_pre.bias"), M, D, false,
-                     true, L, W32(h, "backbone.class_embedding"), W32(h, "backbone.positional_embedding"), st,
+    RET_IF(layernorm(h, patch32, h->x32, h->vw.ln_pre_g, h->vw.ln_pre_b, M, D, false,
+                     true, L, h->vw.cls_emb, h->vw.pos, st,
                      FSAR_K_LAYERNORM));
     // Row direction alternates from kernel to kernel (dir ^= 1): every consumer walks the rows in the opposite order
     // of the producer of its big input (x32 58 MB, qkv16 87 MB, h16 116 MB at 96 frames — together more than the
@@ -644,8 +756,8 @@ int vit_encode_gathered(fsar_handle* h, int n, float* feats_out, cudaStream_t st
     int dir = h->alternate_rows ? 1 : 0;
     const int flip = h->alternate_rows ? 1 : 0;
     for (int i = 0; i < c.layers; ++i) {
-        const std::string pre = "backbone.transformer.resblocks." + std::to_string(i) + ".";
-        RET_IF(layernorm(h, h->x32, h->ln16, W32(h, pre + "ln_1.weight"), W32(h, pre + "ln_1.bias"), M, D, true, false, L,
+        const BlockW& bw = h->vit_blocks[i];
+        RET_IF(layernorm(h, h->x32, h->ln16, bw.ln1_g, bw.ln1_b, M, D, true, false, L,
                          nullptr, nullptr, st, FSAR_K_LAYERNORM, dir));
         dir ^= flip;
         if (i == c.layers - 1 && h->cls_last_block && L <= CLS_ATT_MAX_L) {
@@ -654,8 +766,8 @@ int vit_encode_gathered(fsar_handle* h, int n, float* feats_out, cudaStream_t st
             // CLS row of every frame only -- the same numbers the full block would leave in those rows. Row pitches of
             // L * D address the CLS rows of ln16 / x32 in place.
             const long long cls_pitch = (long long)L * D;
-            const T16* w_in = W16(h, pre + "attn.in_proj_weight");
-            const float* b_in = W32(h, pre + "attn.in_proj_bias");
+            const T16* w_in = bw.w_in;
+            const float* b_in = bw.b_in;
             T16* kv16 = h->qkv16;   // [M, 2 D]
             RET_IF(gemm(h, FSAR_K_GEMM_QKV, h->ln16, w_in + (size_t)D * D, b_in + D, kv16, M, 2 * D, D, EPI_STORE16, st, dir));
             RET_IF(gemm(h, FSAR_K_LAST_BLOCK_CLS, h->ln16, w_in, b_in, h->cls_q16, n, D, D, EPI_STORE16, st, 0, cls_pitch));
@@ -665,31 +777,30 @@ int vit_encode_gathered(fsar_handle* h, int n, float* feats_out, cudaStream_t st
                            (const T16*)kv16, h->cls_att16, L, D, 0.125f * 1.4426950408889634f);
                 RET_IF(check_launch(h, "cls_attention_kernel"));
             }
-            RET_IF(gemm(h, FSAR_K_LAST_BLOCK_CLS, h->cls_att16, W16(h, pre + "attn.out_proj.weight"),
-                        W32(h, pre + "attn.out_proj.bias"), h->x32, n, D, D, EPI_RESID32, st, 0, 0, cls_pitch));
-            RET_IF(layernorm(h, h->x32, h->cls_ln16, W32(h, pre + "ln_2.weight"), W32(h, pre + "ln_2.bias"), n, D, true, false,
+            RET_IF(gemm(h, FSAR_K_LAST_BLOCK_CLS, h->cls_att16, bw.w_out, bw.b_out, h->x32, n, D, D, EPI_RESID32, st, 0, 0, cls_pitch));
+            RET_IF(layernorm(h, h->x32, h->cls_ln16, bw.ln2_g, bw.ln2_b, n, D, true, false,
                              L, nullptr, nullptr, st, FSAR_K_LAST_BLOCK_CLS, 0, cls_pitch));
-            RET_IF(gemm(h, FSAR_K_LAST_BLOCK_CLS, h->cls_ln16, W16(h, pre + "mlp.c_fc.weight"), W32(h, pre + "mlp.c_fc.bias"),
+            RET_IF(gemm(h, FSAR_K_LAST_BLOCK_CLS, h->cls_ln16, bw.w_fc, bw.b_fc,
                         h->cls_h16, n, 4 * D, D, EPI_QGELU16, st));
-            RET_IF(gemm(h, FSAR_K_LAST_BLOCK_CLS, h->cls_h16, W16(h, pre + "mlp.c_proj.weight"), W32(h, pre + "mlp.c_proj.bias"),
+            RET_IF(gemm(h, FSAR_K_LAST_BLOCK_CLS, h->cls_h16, bw.w_proj, bw.b_proj,
                         h->x32, n, D, 4 * D, EPI_RESID32, st, 0, 0, cls_pitch));
             break;
         }
-        RET_IF(gemm(h, FSAR_K_GEMM_QKV, h->ln16, W16(h, pre + "attn.in_proj_weight"), W32(h, pre + "attn.in_proj_bias"),
+        RET_IF(gemm(h, FSAR_K_GEMM_QKV, h->ln16, bw.w_in, bw.b_in,
                     h->qkv16, M, 3 * D, D, EPI_STORE16, st, dir));
         dir ^= flip;
         RET_IF(attention(h, h->qkv16, n, L, c.heads, h->att16, st, dir));
         dir ^= flip;
-        RET_IF(gemm(h, FSAR_K_GEMM_OUT, h->att16, W16(h, pre + "attn.out_proj.weight"), W32(h, pre + "attn.out_proj.bias"),
+        RET_IF(gemm(h, FSAR_K_GEMM_OUT, h->att16, bw.w_out, bw.b_out,
                     h->x32, M, D, D, EPI_RESID32, st, dir));
         dir ^= flip;
-        RET_IF(layernorm(h, h->x32, h->ln16, W32(h, pre + "ln_2.weight"), W32(h, pre + "ln_2.bias"), M, D, true, false, L,
+        RET_IF(layernorm(h, h->x32, h->ln16, bw.ln2_g, bw.ln2_b, M, D, true, false, L,
                          nullptr, nullptr, st, FSAR_K_LAYERNORM, dir));
         dir ^= flip;
-        RET_IF(gemm(h, FSAR_K_GEMM_FC1, h->ln16, W16(h, pre + "mlp.c_fc.weight"), W32(h, pre + "mlp.c_fc.bias"), h->h16, M,
+        RET_IF(gemm(h, FSAR_K_GEMM_FC1, h->ln16, bw.w_fc, bw.b_fc, h->h16, M,
                     4 * D, D, EPI_QGELU16, st, dir));
         dir ^= flip;
-        RET_IF(gemm(h, FSAR_K_GEMM_FC2, h->h16, W16(h, pre + "mlp.c_proj.weight"), W32(h, pre + "mlp.c_proj.bias"), h->x32,
+        RET_IF(gemm(h, FSAR_K_GEMM_FC2, h->h16, bw.w_proj, bw.b_proj, h->x32,
                     M, D, 4 * D, EPI_RESID32, st, dir));
         dir ^= flip;
     }
@@ -697,7 +808,7 @@ int vit_encode_gathered(fsar_handle* h, int n, float* feats_out, cudaStream_t st
         const dim3 grid((n + FINAL_FPC - 1) / FINAL_FPC, (c.embed_dim + FINAL_COLS - 1) / FINAL_COLS);
         Scope s(h, st, FSAR_K_FINAL_PROJ, 2.0 * n * D * c.embed_dim, 4.0 * ((double)D * c.embed_dim + (double)n * D));
         launch_pdl(h, final_proj_kernel, grid, dim3(256), sizeof(float) * FINAL_FPC * D, st,
-                   (const float*)h->x32, W32(h, "backbone.ln_post.weight"), W32(h, "backbone.ln_post.bias"), W32(h, "backbone.proj"),
+                   (const float*)h->x32, h->vw.ln_post_g, h->vw.ln_post_b, h->vw.proj,
                    feats_out, n, L, D, c.embed_dim, 1e-5f);
         RET_IF(check_launch(h, "final_proj_kernel"));
     }
@@ -751,12 +862,12 @@ int modulate_rows(fsar_handle* h, HeadWs& w, const float* x, int n_q, int n_s, i
     if (T + 1 > MOD_MAX_TOK) return fail(h, FSAR_E_INVALID, "modulator: %d tokens per sequence exceeds %d", T + 1, MOD_MAX_TOK);
     const float* cur = x;
     for (int l = 0; l < c.mod_depth; ++l) {
-        const std::string p = "context2.layers." + std::to_string(l) + ".";
+        const ModW& mw = h->mod_layers[l];
         // depth > 1: intermediate layers ping-pong between mod_tmp and seq (seq is dead once layer 0 consumed it)
         float* dst = (l == c.mod_depth - 1) ? out : ((l & 1) ? w.seq : w.mod_tmp);
-        RET_IF(layernorm(h, cur, w.mod_ln, W32(h, p + "0.norm.weight"), W32(h, p + "0.norm.bias"), rows, E, false, false,
+        RET_IF(layernorm(h, cur, w.mod_ln, mw.norm_g, mw.norm_b, rows, E, false, false,
                          1, nullptr, nullptr, st, FSAR_K_MODULATOR));
-        RET_IF(linear_f32<LIN_NONE>(h, w.mod_ln, h->mod_qkv[l], nullptr, nullptr, w.mod_qkvbuf, rows, 3 * inner, E, st));
+        RET_IF(linear_f32<LIN_NONE>(h, w.mod_ln, mw.qkv, nullptr, nullptr, w.mod_qkvbuf, rows, 3 * inner, E, st));
         {
             const int nmax = T + 1, dh = c.mod_dim_head;
             const size_t smem = sizeof(float) * ((size_t)3 * nmax * dh + (size_t)nmax * (nmax + 1));
@@ -766,11 +877,11 @@ int modulate_rows(fsar_handle* h, HeadWs& w, const float* x, int n_q, int n_s, i
                 1.0f / sqrtf((float)dh));
             RET_IF(check_launch(h, "modulator_attention_kernel"));
         }
-        RET_IF(linear_f32<LIN_NONE>(h, w.mod_att, W32(h, p + "0.fn.to_out.0.weight"), W32(h, p + "0.fn.to_out.0.bias"), cur,
+        RET_IF(linear_f32<LIN_NONE>(h, w.mod_att, mw.w_out, mw.b_out, cur,
                                     w.mod_y, rows, E, inner, st));
-        RET_IF(linear_f32<LIN_GELU>(h, w.mod_y, W32(h, p + "1.net.0.weight"), W32(h, p + "1.net.0.bias"), nullptr, w.mod_h,
+        RET_IF(linear_f32<LIN_GELU>(h, w.mod_y, mw.w_fc, mw.b_fc, nullptr, w.mod_h,
                                     rows, F, E, st));
-        RET_IF(linear_f32<LIN_NONE>(h, w.mod_h, W32(h, p + "1.net.3.weight"), W32(h, p + "1.net.3.bias"), w.mod_y, dst,
+        RET_IF(linear_f32<LIN_NONE>(h, w.mod_h, mw.w_proj, mw.b_proj, w.mod_y, dst,
                                     rows, E, F, st));
         cur = dst;
     }
@@ -801,13 +912,14 @@ int head_forward(fsar_handle* h, HeadWs& w, const float* sup, const float* tgt, 
     }
     {
         Scope s(h, st, FSAR_K_HEAD_MISC, 0.0, 8.0 * S);
-        launch_pdl(h, class_index_kernel, dim3(1), dim3(128), 0, st, support_labels, S, w.cls, w.counts, way);
+        launch_pdl(h, class_index_kernel, dim3(1), dim3(128), 0, st, support_labels, S, w.cls, w.counts, way,
+                   real_support_labels, h->n_text_test, h->status_dev);
         RET_IF(check_launch(h, "class_index_kernel"));
     }
     if (text_mode == 1) {   // TRAIN.EVAL_TEXT: text probabilities only, the modulator / OTAM are not evaluated
         Scope s(h, st, FSAR_K_HEAD_MISC, 2.0 * Q * way * E, 4.0 * ((double)Q * T * E + (double)way * E));
-        launch_pdl(h, text_fusion_kernel, dim3(Q), dim3(256), sizeof(float) * E, st, tgt, W32(h, "text_features_test"), real_support_labels, w.cls,
-                                                              w.counts, S, T, E, way, W32(h, "scale"), 1, 0.f, nullptr, logits);
+        launch_pdl(h, text_fusion_kernel, dim3(Q), dim3(256), sizeof(float) * E, st, tgt, h->vw.text_test, real_support_labels, w.cls,
+                                                              w.counts, S, T, E, way, h->n_text_test, h->vw.scale, 1, 0.f, nullptr, logits);
         RET_IF(check_launch(h, "text_fusion_kernel"));
         h->last_S = S; h->last_Q = Q; h->last_T = T; h->last_way = way; h->last_rows = 0;
         h->last_sup = sup; h->last_tgt = tgt;
@@ -817,16 +929,16 @@ int head_forward(fsar_handle* h, HeadWs& w, const float* sup, const float* tgt, 
         if (!find_w(h, "text_features_train")->set) return fail(h, FSAR_E_STATE, "text_features_train has not been set");
         Scope s(h, st, FSAR_K_HEAD_MISC, 2.0 * (S + Q) * h->n_text_train * E,
                 4.0 * ((double)(S + Q) * T * E + (double)h->n_text_train * E));
-        launch_pdl(h, class_text_logits_kernel, dim3(S + Q), dim3(256), sizeof(float) * E, st, sup, S, tgt, Q, T, E, W32(h, "text_features_train"),
-                                                                        h->n_text_train, W32(h, "scale"), class_logits);
+        launch_pdl(h, class_text_logits_kernel, dim3(S + Q), dim3(256), sizeof(float) * E, st, sup, S, tgt, Q, T, E, h->vw.text_train,
+                                                                        h->n_text_train, h->vw.scale, class_logits);
         RET_IF(check_launch(h, "class_text_logits_kernel"));
     }
     const int n_sup_seq = merge_before ? way : S;
     const int rows = Q * T + n_sup_seq * (T + 1);
     {
         Scope s(h, st, FSAR_K_HEAD_MISC, 0.0, 8.0 * rows * E);
-        launch_pdl(h, build_sequences_kernel, dim3(rows), dim3(128), 0, st, sup, tgt, W32(h, "text_features_test"), real_support_labels, w.cls,
-                                                     w.counts, S, Q, T, E, way, merge_before, w.seq);
+        launch_pdl(h, build_sequences_kernel, dim3(rows), dim3(128), 0, st, sup, tgt, h->vw.text_test, real_support_labels, w.cls,
+                                                     w.counts, S, Q, T, E, way, merge_before, h->n_text_test, w.seq);
         RET_IF(check_launch(h, "build_sequences_kernel"));
     }
     // depth > 1 uses w.seq as a ping-pong buffer, so the first layer must not read it after layer 2 wrote it:
@@ -841,8 +953,8 @@ int head_forward(fsar_handle* h, HeadWs& w, const float* sup, const float* tgt, 
     RET_IF(otam_logits(h, w.mod_out, w.protos, Q, way, T, single_direct, logits, w.dists, w.cum, st));
     if (text_mode == 2) {   // TRAIN.COMBINE: geometric fusion of text and visual probabilities overwrites the logits
         Scope s(h, st, FSAR_K_HEAD_MISC, 2.0 * Q * way * E, 4.0 * ((double)Q * T * E + (double)way * E));
-        launch_pdl(h, text_fusion_kernel, dim3(Q), dim3(256), sizeof(float) * E, st, tgt, W32(h, "text_features_test"), real_support_labels, w.cls,
-                                                              w.counts, S, T, E, way, W32(h, "scale"), 2, text_coff, w.cum,
+        launch_pdl(h, text_fusion_kernel, dim3(Q), dim3(256), sizeof(float) * E, st, tgt, h->vw.text_test, real_support_labels, w.cls,
+                                                              w.counts, S, T, E, way, h->n_text_test, h->vw.scale, 2, text_coff, w.cum,
                                                               logits);
         RET_IF(check_launch(h, "text_fusion_kernel"));
     }
@@ -895,6 +1007,9 @@ int episodes_forward_dev(fsar_handle* h, const fsar_episode* eps, int n, float* 
         const float* tgt = sup + (size_t)ep.n_support * T * E;
         cudaStream_t hs = fork ? h->head_streams[i] : st;
         if (fork) CU_OK(h, cudaStreamWaitEvent(hs, h->head_fork, 0));
+        if (class_logits != nullptr && ep.text_mode != 0 && h->n_text_train > 0)   // the reference returns None there:
+            CU_OK(h, cudaMemsetAsync(class_logits + c_off, 0,                     // the slice reads as zeros, never as stale memory
+                                     sizeof(float) * (size_t)(ep.n_support + ep.n_target) * h->n_text_train, hs));
         RET_IF(head_forward(h, h->ws[i], sup, tgt, ep.support_labels, ep.real_support_labels, ep.n_support, ep.n_target, T,
                             ep.way, ep.merge_before, ep.single_direct, ep.text_mode, ep.text_coff, logits + l_off,
                             class_logits ? class_logits + c_off : nullptr, hs));
@@ -979,7 +1094,12 @@ int fsar_create(const fsar_config* cfg, fsar_handle** out) {
     h->patch_k = 3 * c.patch_size * c.patch_size;
     h->patch_kp = round_up(h->patch_k, GEMM_BK);
     {
-        const char* e = getenv("FSAR_LEGACY_ATTENTION");
+        const char* e = getenv("FSAR_FULL_LAST_BLOCK");
+        h->cls_last_block = !(e != nullptr && e[0] == '1');
+        e = getenv("FSAR_NO_PDL");
+        h->pdl = !(e != nullptr && e[0] == '1');
+#ifdef FSAR_PROBES
+        e = getenv("FSAR_LEGACY_ATTENTION");
         h->legacy_attention = (e != nullptr && e[0] == '1');
         e = getenv("FSAR_NO_ALTERNATE");
         h->alternate_rows = !(e != nullptr && e[0] == '1');
@@ -987,14 +1107,14 @@ int fsar_create(const fsar_config* cfg, fsar_handle** out) {
         h->single_cta_gemm = (e != nullptr && e[0] == '1');
         e = getenv("FSAR_GEMM_DEBUG");
         h->gemm_debug = e != nullptr ? atoi(e) : 0;
+        e = getenv("FSAR_ATT_DEBUG");
+        h->att_debug = e != nullptr ? atoi(e) : 0;
         e = getenv("FSAR_SMALL_M");
         if (e != nullptr) h->small_m = atoi(e);
-        e = getenv("FSAR_FULL_LAST_BLOCK");
-        h->cls_last_block = !(e != nullptr && e[0] == '1');
-        e = getenv("FSAR_NO_PDL");
-        h->pdl = !(e != nullptr && e[0] == '1');
+#endif
     }
     int rc = 0;
+    DeviceGuard guard(h);
     do {
         if (cudaSetDevice(c.device) != cudaSuccess) { rc = fail(nullptr, FSAR_E_CUDA, "cudaSetDevice(%d) failed", c.device); break; }
         void* fn = nullptr;
@@ -1022,6 +1142,12 @@ int fsar_create(const fsar_config* cfg, fsar_handle** out) {
         }
         if ((rc = alloc_weights(h)) != 0) break;
         if ((rc = alloc_workspace(h)) != 0) break;
+        if (cudaHostAlloc(reinterpret_cast<void**>(&h->status_host), 64, cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->status_dev), h->status_host, 0) != cudaSuccess) {
+            rc = fail(nullptr, FSAR_E_NOMEM, "cannot allocate the mapped status word");
+            break;
+        }
+        memset(h->status_host, 0, 64);
     } while (0);
     if (rc != 0) {
         if (!h->err.empty()) g_create_error = h->err;
@@ -1034,6 +1160,8 @@ int fsar_create(const fsar_config* cfg, fsar_handle** out) {
 
 void fsar_destroy(fsar_handle* h) {
     if (h == nullptr) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
     for (auto& w : h->w) {
@@ -1064,10 +1192,12 @@ void fsar_destroy(fsar_handle* h) {
         if (s.copied) cudaEventDestroy(s.copied);
         if (s.done) cudaEventDestroy(s.done);
     }
+    if (h->status_host) cudaFreeHost(h->status_host);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
     for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     delete h;
+    if (prev >= 0) cudaSetDevice(prev);
 }
 
 int fsar_set_weight(fsar_handle* h, const char* name, const float* data, int64_t numel, int on_device) {
@@ -1084,14 +1214,19 @@ int fsar_set_weight(fsar_handle* h, const char* name, const float* data, int64_t
     } else if (numel != w->numel) {
         return fail(h, FSAR_E_INVALID, "%s: expected %lld elements, got %lld", name, (long long)w->numel, (long long)numel);
     }
-    CU_OK(h, cudaSetDevice(h->cfg.device));
+    DeviceGuard guard(h);
+    // Ordering contract (fsar.h): the copy runs on the legacy default stream, which does not order against the library's
+    // non-blocking compute / copy / head streams nor against a caller's own streams. So: wait for everything in flight
+    // on the device (no forward may still be reading the old weights), copy + re-pack, and wait again (the next
+    // forward on any stream sees the new ones). Weight updates are rare; forwards never synchronise.
+    CU_OK(h, cudaDeviceSynchronize());
     CU_OK(h, cudaMemcpy(w->d32, data, sizeof(float) * (size_t)numel, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
     if (w->d16 != nullptr) {
         const long long n = (long long)w->rows * w->kp;
         pack_weight_kernel<<<(int)((n + 255) / 256), 256>>>(w->d32, w->d16, w->rows, w->cols, w->kp);
         RET_IF(check_launch(h, "pack_weight_kernel"));
-        CU_OK(h, cudaDeviceSynchronize());
     }
+    CU_OK(h, cudaDeviceSynchronize());
     w->set = true;
     return 0;
 }
@@ -1111,6 +1246,7 @@ const char* fsar_missing_weight(const fsar_handle* h, int i) {
 }
 
 int fsar_vit_forward(fsar_handle* h, const float* frames_dev, int n_frames, float* feats_dev, void* stream) {
+    DeviceGuard guard(h);
     if (h == nullptr || frames_dev == nullptr || feats_dev == nullptr || n_frames < 1)
         return fail(h, FSAR_E_INVALID, "fsar_vit_forward: bad argument");
     if (!ready(h, false)) return fail(h, FSAR_E_STATE, "%d weights have not been set (first: %s)", fsar_missing_weights(h), fsar_missing_weight(h, 0));
@@ -1118,6 +1254,7 @@ int fsar_vit_forward(fsar_handle* h, const float* frames_dev, int n_frames, floa
 }
 
 int fsar_modulate(fsar_handle* h, const float* x_dev, int n_seq, int n_tok, float* out_dev, void* stream) {
+    DeviceGuard guard(h);
     if (h == nullptr || x_dev == nullptr || out_dev == nullptr || n_seq < 1 || n_tok < 1)
         return fail(h, FSAR_E_INVALID, "fsar_modulate: bad argument");
     if (!ready(h, false)) return fail(h, FSAR_E_STATE, "%d weights have not been set", fsar_missing_weights(h));
@@ -1129,6 +1266,7 @@ int fsar_modulate(fsar_handle* h, const float* x_dev, int n_seq, int n_tok, floa
 
 int fsar_otam_logits(fsar_handle* h, const float* q_dev, const float* protos_dev, int Q, int way, int T, int single_direct,
                      float* logits_dev, float* dists_dev, float* cum_dev, void* stream) {
+    DeviceGuard guard(h);
     if (h == nullptr || q_dev == nullptr || protos_dev == nullptr || logits_dev == nullptr || Q < 1 || way < 1)
         return fail(h, FSAR_E_INVALID, "fsar_otam_logits: bad argument");
     return otam_logits(h, q_dev, protos_dev, Q, way, T, single_direct, logits_dev, dists_dev, cum_dev, (cudaStream_t)stream);
@@ -1136,7 +1274,9 @@ int fsar_otam_logits(fsar_handle* h, const float* q_dev, const float* protos_dev
 
 int fsar_episodes_forward(fsar_handle* h, const fsar_episode* eps, int n_episodes, float* logits_dev,
                           float* class_logits_dev, void* stream) {
+    DeviceGuard guard(h);
     if (h == nullptr || logits_dev == nullptr) return fail(h, FSAR_E_INVALID, "fsar_episodes_forward: NULL argument");
+    RET_IF(check_status(h));   // labels of EARLIER stream-ordered episodes (this call does not synchronise either)
     RET_IF(check_batch(h, eps, n_episodes));
     return episodes_forward_dev(h, eps, n_episodes, logits_dev, class_logits_dev, (cudaStream_t)stream);
 }
@@ -1146,9 +1286,9 @@ int fsar_episode_forward(fsar_handle* h, const fsar_episode* ep, float* logits_d
 }
 
 int fsar_episodes_submit_host(fsar_handle* h, int slot, const fsar_episode* eps, int n_episodes) {
+    DeviceGuard guard(h);
     if (h == nullptr || slot < 0 || slot > 1) return fail(h, FSAR_E_INVALID, "fsar_episodes_submit_host: bad argument");
     RET_IF(check_batch(h, eps, n_episodes));
-    CU_OK(h, cudaSetDevice(h->cfg.device));
     RET_IF(ensure_host_path(h));
     HostSlot& s = h->slot[slot];
     if (s.busy) return fail(h, FSAR_E_STATE, "slot %d still holds uncollected episodes", slot);
@@ -1184,11 +1324,13 @@ int fsar_episodes_submit_host(fsar_handle* h, int slot, const fsar_episode* eps,
 }
 
 int fsar_episodes_collect_host(fsar_handle* h, int slot, float* logits_host, float* class_logits_host) {
+    DeviceGuard guard(h);
     if (h == nullptr || slot < 0 || slot > 1) return fail(h, FSAR_E_INVALID, "fsar_episodes_collect_host: bad argument");
     HostSlot& s = h->slot[slot];
     if (!s.busy) return fail(h, FSAR_E_STATE, "slot %d holds no submitted episode", slot);
     CU_OK(h, cudaEventSynchronize(s.done));
     s.busy = 0;
+    RET_IF(check_status(h));   // the slot's kernels have run: a bad label of THIS batch is reported here
     if (logits_host) memcpy(logits_host, s.logits_pin, sizeof(float) * s.n_logits);
     if (class_logits_host) memcpy(class_logits_host, s.clogits_pin, sizeof(float) * s.n_clogits);
     return 0;
@@ -1221,15 +1363,16 @@ static int preprocess_u8(fsar_handle* h, const uint8_t* src, int n, int H, int W
 
 int fsar_preprocess_u8(fsar_handle* h, const uint8_t* frames_u8_dev, int n_frames, int H, int W, int resize_h, int resize_w,
                        const float mean[3], const float std[3], float* out_dev, void* stream) {
+    DeviceGuard guard(h);
     if (h == nullptr || frames_u8_dev == nullptr || out_dev == nullptr) return fail(h, FSAR_E_INVALID, "fsar_preprocess_u8: NULL argument");
     return preprocess_u8(h, frames_u8_dev, n_frames, H, W, resize_h, resize_w, mean, std, out_dev, (cudaStream_t)stream);
 }
 
 int fsar_episodes_submit_host_u8(fsar_handle* h, int slot, const fsar_episode* eps, int n_episodes, int H, int W,
                                  int resize_h, int resize_w, const float mean[3], const float std[3]) {
+    DeviceGuard guard(h);
     if (h == nullptr || slot < 0 || slot > 1) return fail(h, FSAR_E_INVALID, "fsar_episodes_submit_host_u8: bad argument");
     RET_IF(check_batch(h, eps, n_episodes));
-    CU_OK(h, cudaSetDevice(h->cfg.device));
     RET_IF(ensure_host_path(h));
     HostSlot& s = h->slot[slot];
     if (s.busy) return fail(h, FSAR_E_STATE, "slot %d still holds uncollected episodes", slot);
@@ -1272,13 +1415,13 @@ int fsar_episodes_submit_host_u8(fsar_handle* h, int slot, const fsar_episode* e
 }
 
 int fsar_text_configure(fsar_handle* h, const fsar_text_config* tc) {
+    DeviceGuard guard(h);
     if (h == nullptr || tc == nullptr) return fail(h, FSAR_E_INVALID, "fsar_text_configure: NULL argument");
     if (h->text_cfg.width != 0) return fail(h, FSAR_E_STATE, "the text tower is already configured");
     if (tc->width % 128 != 0 || tc->width > 1024 || tc->heads * ATT_HD != tc->width || tc->layers < 1 ||
         tc->context_length < 1 || tc->context_length > ATT5_MAX_KEYS || tc->vocab_size < 1)
         return fail(h, FSAR_E_INVALID, "unsupported text tower (width %d, heads %d, layers %d, context %d, vocab %d)",
                     tc->width, tc->heads, tc->layers, tc->context_length, tc->vocab_size);
-    CU_OK(h, cudaSetDevice(h->cfg.device));
     const int W = tc->width, E = h->cfg.embed_dim;
     const size_t first = h->w.size();
     add_w(h, "clip.token_embedding.weight", (int64_t)tc->vocab_size * W, 0, 0, 0, false);
@@ -1304,10 +1447,17 @@ int fsar_text_configure(fsar_handle* h, const fsar_text_config* tc) {
     for (size_t i = first; i < h->w.size(); ++i) h->w[i].tower = true;
     RET_IF(alloc_weight_storage(h));
     h->text_cfg = *tc;
+    resolve_blocks(h, "clip.", tc->layers, &h->text_blocks);
+    h->tw.tok = W32(h, "clip.token_embedding.weight");
+    h->tw.pos = W32(h, "clip.positional_embedding");
+    h->tw.lnf_g = W32(h, "clip.ln_final.weight");
+    h->tw.lnf_b = W32(h, "clip.ln_final.bias");
+    h->tw.proj = W32(h, "clip.text_projection");
     return 0;
 }
 
 int fsar_text_encode(fsar_handle* h, const int32_t* tokens_dev, int n_texts, float* out_dev, void* stream) {
+    DeviceGuard guard(h);
     if (h == nullptr || tokens_dev == nullptr || out_dev == nullptr || n_texts < 1)
         return fail(h, FSAR_E_INVALID, "fsar_text_encode: bad argument");
     const fsar_text_config& t = h->text_cfg;
@@ -1327,30 +1477,29 @@ int fsar_text_encode(fsar_handle* h, const int32_t* tokens_dev, int n_texts, flo
         const int* tok = tokens_dev + (size_t)done * C;
         {
             Scope s(h, st, FSAR_K_HEAD_MISC, 0.0, 12.0 * M * W);
-            text_embed_kernel<<<(M + 7) / 8, 256, 0, st>>>(tok, W32(h, "clip.token_embedding.weight"),
-                                                           W32(h, "clip.positional_embedding"), h->x32, M, C, W, t.vocab_size);
+            text_embed_kernel<<<(M + 7) / 8, 256, 0, st>>>(tok, h->tw.tok, h->tw.pos, h->x32, M, C, W, t.vocab_size);
             RET_IF(check_launch(h, "text_embed_kernel"));
         }
         for (int i = 0; i < t.layers; ++i) {
-            const std::string pre = "clip.transformer.resblocks." + std::to_string(i) + ".";
-            RET_IF(layernorm(h, h->x32, h->ln16, W32(h, pre + "ln_1.weight"), W32(h, pre + "ln_1.bias"), M, W, true, false, C,
+            const BlockW& bw = h->text_blocks[i];
+            RET_IF(layernorm(h, h->x32, h->ln16, bw.ln1_g, bw.ln1_b, M, W, true, false, C,
                              nullptr, nullptr, st, FSAR_K_LAYERNORM));
-            RET_IF(gemm(h, FSAR_K_GEMM_QKV, h->ln16, W16(h, pre + "attn.in_proj_weight"), W32(h, pre + "attn.in_proj_bias"),
+            RET_IF(gemm(h, FSAR_K_GEMM_QKV, h->ln16, bw.w_in, bw.b_in,
                         h->qkv16, M, 3 * W, W, EPI_STORE16, st));
             RET_IF(attention(h, h->qkv16, n, C, t.heads, h->att16, st, 0, /*causal=*/1));
-            RET_IF(gemm(h, FSAR_K_GEMM_OUT, h->att16, W16(h, pre + "attn.out_proj.weight"), W32(h, pre + "attn.out_proj.bias"),
+            RET_IF(gemm(h, FSAR_K_GEMM_OUT, h->att16, bw.w_out, bw.b_out,
                         h->x32, M, W, W, EPI_RESID32, st));
-            RET_IF(layernorm(h, h->x32, h->ln16, W32(h, pre + "ln_2.weight"), W32(h, pre + "ln_2.bias"), M, W, true, false, C,
+            RET_IF(layernorm(h, h->x32, h->ln16, bw.ln2_g, bw.ln2_b, M, W, true, false, C,
                              nullptr, nullptr, st, FSAR_K_LAYERNORM));
-            RET_IF(gemm(h, FSAR_K_GEMM_FC1, h->ln16, W16(h, pre + "mlp.c_fc.weight"), W32(h, pre + "mlp.c_fc.bias"), h->h16, M,
+            RET_IF(gemm(h, FSAR_K_GEMM_FC1, h->ln16, bw.w_fc, bw.b_fc, h->h16, M,
                         4 * W, W, EPI_QGELU16, st));
-            RET_IF(gemm(h, FSAR_K_GEMM_FC2, h->h16, W16(h, pre + "mlp.c_proj.weight"), W32(h, pre + "mlp.c_proj.bias"), h->x32,
+            RET_IF(gemm(h, FSAR_K_GEMM_FC2, h->h16, bw.w_proj, bw.b_proj, h->x32,
                         M, W, 4 * W, EPI_RESID32, st));
         }
         {
             Scope s(h, st, FSAR_K_FINAL_PROJ, 2.0 * n * W * E, 4.0 * ((double)W * E + (double)n * W));
-            text_final_kernel<<<n, 256, sizeof(float) * W, st>>>(h->x32, tok, W32(h, "clip.ln_final.weight"),
-                                                                 W32(h, "clip.ln_final.bias"), W32(h, "clip.text_projection"),
+            text_final_kernel<<<n, 256, sizeof(float) * W, st>>>(h->x32, tok, h->tw.lnf_g,
+                                                                 h->tw.lnf_b, h->tw.proj,
                                                                  out_dev + (size_t)done * E, C, W, E, 1e-5f);
             RET_IF(check_launch(h, "text_final_kernel"));
         }
@@ -1360,6 +1509,7 @@ int fsar_text_encode(fsar_handle* h, const int32_t* tokens_dev, int n_texts, flo
 
 int fsar_metrics_update(fsar_handle* h, const float* logits_dev, const float* target_labels_dev, int Q, int way,
                         int64_t* counters_dev, int64_t* per_class_dev, void* stream) {
+    DeviceGuard guard(h);
     if (h == nullptr || logits_dev == nullptr || target_labels_dev == nullptr || counters_dev == nullptr || Q < 1 || way < 1)
         return fail(h, FSAR_E_INVALID, "fsar_metrics_update: bad argument");
     Scope s(h, (cudaStream_t)stream, FSAR_K_HEAD_MISC, 0.0, 4.0 * Q * (way + 1));
@@ -1370,6 +1520,7 @@ int fsar_metrics_update(fsar_handle* h, const float* logits_dev, const float* ta
 }
 
 int64_t fsar_peek(fsar_handle* h, const char* name, void* dst_host, int64_t numel, void* stream) {
+    DeviceGuard guard(h);
     if (h == nullptr || name == nullptr || dst_host == nullptr) return fail(h, FSAR_E_INVALID, "fsar_peek: NULL argument");
     const int E = h->cfg.embed_dim, S = h->last_S, Q = h->last_Q, T = h->last_T, way = h->last_way;
     const void* src = nullptr;
@@ -1395,6 +1546,7 @@ int64_t fsar_peek(fsar_handle* h, const char* name, void* dst_host, int64_t nume
 
 int fsar_op_layernorm(fsar_handle* h, const float* x_dev, const float* gamma_dev, const float* beta_dev, int rows, int dim,
                       int out16, void* out_dev, void* stream) {
+    DeviceGuard guard(h);
     if (h == nullptr || x_dev == nullptr || out_dev == nullptr || rows < 1) return fail(h, FSAR_E_INVALID, "fsar_op_layernorm: bad argument");
     return layernorm(h, x_dev, out_dev, gamma_dev, beta_dev, rows, dim, out16 != 0, false, 1, nullptr, nullptr,
                      (cudaStream_t)stream, FSAR_K_LAYERNORM);
@@ -1402,18 +1554,21 @@ int fsar_op_layernorm(fsar_handle* h, const float* x_dev, const float* gamma_dev
 
 int fsar_op_gemm(fsar_handle* h, const void* a16_dev, const void* w16_dev, const float* bias_dev, int M, int N, int K, int epi,
                  void* out_dev, void* stream) {
+    DeviceGuard guard(h);
     if (h == nullptr || a16_dev == nullptr || w16_dev == nullptr || out_dev == nullptr) return fail(h, FSAR_E_INVALID, "fsar_op_gemm: NULL argument");
     return gemm(h, FSAR_K_GEMM_QKV, (const T16*)a16_dev, (const T16*)w16_dev, bias_dev, out_dev, M, N, K, epi,
                 (cudaStream_t)stream);
 }
 
 int fsar_op_attention(fsar_handle* h, const void* qkv16_dev, int n_frames, int L, int heads, void* out16_dev, void* stream) {
+    DeviceGuard guard(h);
     if (h == nullptr || qkv16_dev == nullptr || out16_dev == nullptr || n_frames < 1 || L < 1 || heads < 1)
         return fail(h, FSAR_E_INVALID, "fsar_op_attention: bad argument");
     return attention(h, (const T16*)qkv16_dev, n_frames, L, heads, (T16*)out16_dev, (cudaStream_t)stream);
 }
 
 int fsar_op_f32_to_16(fsar_handle* h, const float* src_dev, void* dst16_dev, int64_t numel, void* stream) {
+    DeviceGuard guard(h);
     if (h == nullptr || src_dev == nullptr || dst16_dev == nullptr || numel < 1) return fail(h, FSAR_E_INVALID, "fsar_op_f32_to_16: bad argument");
     const long long groups = (numel + 3) / 4;
     Scope s(h, (cudaStream_t)stream, FSAR_K_HEAD_MISC, 0.0, 6.0 * numel);
@@ -1432,6 +1587,7 @@ int fsar_profile_begin(fsar_handle* h) {
 }
 
 int fsar_profile_end(fsar_handle* h, fsar_profile* out) {
+    DeviceGuard guard(h);
     if (h == nullptr || out == nullptr) return fail(h, FSAR_E_INVALID, "fsar_profile_end: NULL argument");
     h->profiling = false;
     CU_OK(h, cudaDeviceSynchronize());

@@ -19,13 +19,29 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Class index of every support video: cls[s] = rank of labels[s] among the sorted distinct labels
 // (torch.unique(support_labels) is sorted, few_shot.py:2950/2960/2965); counts[c] = shots of class c.
 // Single CTA; S is small (way * shot).
+// It also validates the labels the later kernels index with (the reference fails with an IndexError at
+// text_features_test[support_real_class.long()], few_shot.py:2946): a real label outside [0, n_text) -- negative, NaN,
+// or beyond the rows that were set -- sets status[0] (mapped host memory, read by the host after the next
+// event wait), more distinct labels than `way` sets status[1]. The indexing kernels clamp, so nothing reads out of bounds.
+__device__ __forceinline__ int text_row(float label, int n_text) {
+    const long long v = (long long)label;   // .long() truncation
+    return v < 0 ? 0 : (v >= n_text ? n_text - 1 : (int)v);
+}
 __global__ void class_index_kernel(const float* __restrict__ labels, int S, int* __restrict__ cls,
-                                   int* __restrict__ counts, int way) {
+                                   int* __restrict__ counts, int way, const float* __restrict__ real_labels, int n_text,
+                                   int* status) {
     pdl_trigger();   // programmatic dependent launch: see ptx.cuh
     pdl_wait();
     for (int c = threadIdx.x; c < way; c += blockDim.x) counts[c] = 0;
     __syncthreads();
     for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        if (real_labels != nullptr && status != nullptr) {
+            const float rl = real_labels[s];
+            if (!(rl >= 0.f && rl < float(n_text))) {
+                reinterpret_cast<volatile int*>(status)[0] = 1;
+                __threadfence_system();
+            }
+        }
         const long long ls = (long long)labels[s];  // .long() truncation
         int rank = 0;
         for (int a = 0; a < S; ++a) {
@@ -38,7 +54,12 @@ __global__ void class_index_kernel(const float* __restrict__ labels, int S, int*
             }
         }
         cls[s] = rank;
-        if (rank < way) atomicAdd(&counts[rank], 1);
+        if (rank < way) {
+            atomicAdd(&counts[rank], 1);
+        } else if (status != nullptr) {
+            reinterpret_cast<volatile int*>(status)[1] = 1;
+            __threadfence_system();
+        }
     }
 }
 
@@ -94,7 +115,7 @@ class_text_logits_kernel(const float* __restrict__ sup, int S, const float* __re
 __global__ void __launch_bounds__(128)
 build_sequences_kernel(const float* __restrict__ sup, const float* __restrict__ tgt, const float* __restrict__ text_test,
                        const float* __restrict__ real_labels, const int* __restrict__ cls, const int* __restrict__ counts,
-                       int S, int Q, int T, int E, int way, int merge_before, float* __restrict__ seq) {
+                       int S, int Q, int T, int E, int way, int merge_before, int n_text, float* __restrict__ seq) {
     pdl_trigger();   // programmatic dependent launch: see ptx.cuh
     pdl_wait();
     const int row = blockIdx.x;
@@ -108,7 +129,7 @@ build_sequences_kernel(const float* __restrict__ sup, const float* __restrict__ 
     const int sq = r / (T + 1), tok = r - sq * (T + 1);
     if (!merge_before) {
         const float* src = (tok < T) ? sup + ((size_t)sq * T + tok) * E
-                                     : text_test + (size_t)((long long)real_labels[sq]) * E;
+                                     : text_test + (size_t)text_row(real_labels[sq], n_text) * E;
         for (int e = threadIdx.x; e < E; e += blockDim.x) dst[e] = src[e];
     } else {
         const float inv = 1.0f / float(counts[sq]);
@@ -117,7 +138,7 @@ build_sequences_kernel(const float* __restrict__ sup, const float* __restrict__ 
             for (int s = 0; s < S; ++s) {
                 if (cls[s] == sq) {
                     a += (tok < T) ? sup[((size_t)s * T + tok) * E + e]
-                                   : text_test[(size_t)((long long)real_labels[s]) * E + e];
+                                   : text_test[(size_t)text_row(real_labels[s], n_text) * E + e];
                 }
             }
             dst[e] = a * inv;
@@ -344,7 +365,7 @@ constexpr int TEXT_MAX_WAY = 64;
 __global__ void __launch_bounds__(256)
 text_fusion_kernel(const float* __restrict__ tgt /*[Q,T,E]*/, const float* __restrict__ text_test,
                    const float* __restrict__ real_labels, const int* __restrict__ cls, const int* __restrict__ counts,
-                   int S, int T, int E, int way, const float* __restrict__ scale, int mode, float text_coff,
+                   int S, int T, int E, int way, int n_text, const float* __restrict__ scale, int mode, float text_coff,
                    const float* __restrict__ cum_visual /*[Q,way] or null*/, float* __restrict__ logits /*[Q,way]*/) {
     pdl_trigger();   // programmatic dependent launch: see ptx.cuh
     pdl_wait();
@@ -374,7 +395,7 @@ text_fusion_kernel(const float* __restrict__ tgt /*[Q,T,E]*/, const float* __res
         for (int e = lane; e < E; e += 32) {
             float tv = 0.f;
             for (int s = 0; s < S; ++s)
-                if (cls[s] == c) tv += text_test[(size_t)((long long)real_labels[s]) * E + e];
+                if (cls[s] == c) tv += text_test[(size_t)text_row(real_labels[s], n_text) * E + e];
             tv *= inv;
             dot = fmaf(sm[e], tv, dot);
             tn = fmaf(tv, tv, tn);

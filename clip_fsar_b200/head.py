@@ -234,15 +234,16 @@ class CNN_OTAM_CLIPFSAR_SM100(nn.Module):
         self._mark_dirty()
 
     def _ensure_engine(self, device, n_videos):
-        if self._engine is not None and n_videos > self._engine.cfg.max_videos:
-            self._engine.close()
+        dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        if self._engine is not None and (n_videos > self._engine.cfg.max_videos or self._engine.cfg.device != dev_index):
+            self._engine.close()          # grown episode, or the module moved to another GPU (module.to / DDP device_ids)
             self._engine = None
         if self._engine is None:
             cap = max(n_videos, self._max_videos, 10)
             g = dict(self.geometry)
             n_cls = max(self.text_features_train.shape[0], self.text_features_test.shape[0], 1)
             g.update(max_frames=min(cap * self.num_frames, 384), max_videos=cap, max_tokens=self.num_frames,
-                     max_classes=n_cls, otam_lambda=0.5, device=device.index if device.index is not None else 0)
+                     max_classes=n_cls, otam_lambda=0.5, device=dev_index)
             self._engine = _lib.Engine(**g)
             self._pushed_versions = None
             if self._text_tokens is not None:
@@ -278,9 +279,21 @@ class CNN_OTAM_CLIPFSAR_SM100(nn.Module):
         support, target = inputs["support_set"], inputs["target_set"]
         if not support.is_cuda:
             raise _lib.FsarError(-2, "inputs are on %s: libfsar_sm100 has no CPU path (needs an sm_100 GPU)" % support.device)
+        S_img = self.geometry["image_size"]
+        for name, t in (("support_set", support), ("target_set", target)):
+            if t.dim() != 4 or tuple(t.shape[1:]) != (3, S_img, S_img):
+                # the reference fails here with a positional_embedding shape mismatch (few_shot.py:676)
+                raise ValueError("%s has shape %s but %s expects frames of [3, %d, %d]: set DATA.TEST_CROP_SIZE / "
+                                 "DATA.TRAIN_CROP_SIZE to %d" % (name, tuple(t.shape), self.args.VIDEO.HEAD.BACKBONE_NAME,
+                                                                 S_img, S_img, S_img))
         support_labels = inputs["support_labels"]
         real = inputs["real_support_labels"]
+        if self.text_features_test.shape[0] < 1:
+            raise ValueError("text_features_test is empty: TEST.CLASS_NAME must list the test classes")
         T = self.num_frames
+        if support.shape[0] % T or target.shape[0] % T:
+            raise ValueError("frame counts %d / %d are not multiples of DATA.NUM_INPUT_FRAMES = %d" %
+                             (support.shape[0], target.shape[0], T))
         S, Q = support.shape[0] // T, target.shape[0] // T
         if "batch_class_list" in inputs and inputs["batch_class_list"].numel() > 0:
             way = int(inputs["batch_class_list"].numel())          # shape-derived: no host sync

@@ -160,6 +160,7 @@ class Engine:
         if rc != 0:
             raise FsarError(rc, (self.lib.fsar_last_error(None) or b"").decode())
         self.device = torch.device("cuda", self.cfg.device)
+        self._slot_refs = {}       # host tensors of the batches in flight, per slot (released at collect)
         self.operand_dtype = torch.bfloat16 if self.lib.fsar_operand_dtype() == 1 else torch.float16
 
     # ------------------------------------------------------------------ plumbing
@@ -219,6 +220,9 @@ class Engine:
     # ------------------------------------------------------------------ the path
     def vit_forward(self, frames):
         torch = self._torch
+        S = self.cfg.image_size
+        if frames.dim() != 4 or tuple(frames.shape[1:]) != (3, S, S):
+            raise ValueError("frames must be [n, 3, %d, %d] for this engine, got %s" % (S, S, tuple(frames.shape)))
         n = frames.shape[0]
         out = torch.empty((n, self.cfg.embed_dim), dtype=torch.float32, device=self.device)
         self._check(self.lib.fsar_vit_forward(self._h, self._f32(frames, "frames"), n, c_void_p(out.data_ptr()),
@@ -246,7 +250,13 @@ class Engine:
         return (logits, dists, cum) if return_intermediates else logits
 
     def _episode(self, support, target, support_labels, real_support_labels, n_frames, way, merge_before,
-                 single_direct, text_mode=0, text_coff=0.9):
+                 single_direct, text_mode=0, text_coff=0.9, frame_shape=None):
+        if frame_shape is None:
+            frame_shape = (3, self.cfg.image_size, self.cfg.image_size)
+        for name, t in (("support_set", support), ("target_set", target)):
+            if t.dim() != 4 or tuple(t.shape[1:]) != tuple(frame_shape):
+                raise ValueError("%s must be [frames, %d, %d, %d] for this engine (DATA.TEST_CROP_SIZE / image_size %d), "
+                                 "got %s" % ((name,) + tuple(frame_shape) + (self.cfg.image_size, tuple(t.shape))))
         S = support.shape[0] // n_frames
         Q = target.shape[0] // n_frames
         if S * n_frames != support.shape[0] or Q * n_frames != target.shape[0]:
@@ -255,6 +265,10 @@ class Engine:
         if support_labels.numel() != S or real_support_labels.numel() != S:
             raise ValueError("expected %d support labels, got %d / %d" %
                              (S, support_labels.numel(), real_support_labels.numel()))
+        for name, t in (("support_labels", support_labels), ("real_support_labels", real_support_labels)):
+            if t.dtype != self._torch.float32 or not t.is_contiguous():
+                raise ValueError("%s must be contiguous fp32 (labels are fp32 tensors holding integers, "
+                                 "ssv2_few_shot.py:278-283), got %s" % (name, t.dtype))
         ep = FsarEpisode(support.data_ptr(), target.data_ptr(), support_labels.data_ptr(),
                          real_support_labels.data_ptr(), S, Q, n_frames, way, int(bool(merge_before)),
                          int(bool(single_direct)), int(text_mode), float(text_coff))
@@ -307,12 +321,16 @@ class Engine:
         for i, (sup, tgt, sl, rl) in enumerate(episodes):
             arr[i], S, Q = self._host_episode(sup, tgt, sl, rl, n_frames, way, merge_before, single_direct)
         self._check(self.lib.fsar_episodes_submit_host(self._h, slot, arr, n))
+        self._slot_refs[slot] = list(episodes)      # fsar.h lifetime rule: the buffers live until collect returns
         return n, S, Q
 
     def episodes_collect_host(self, slot, logits_out, class_logits_out=None):
-        self._check(self.lib.fsar_episodes_collect_host(
-            self._h, slot, c_void_p(logits_out.data_ptr()),
-            c_void_p(class_logits_out.data_ptr()) if class_logits_out is not None else None))
+        try:
+            self._check(self.lib.fsar_episodes_collect_host(
+                self._h, slot, c_void_p(logits_out.data_ptr()),
+                c_void_p(class_logits_out.data_ptr()) if class_logits_out is not None else None))
+        finally:
+            self._slot_refs.pop(slot, None)
 
     def _host_episode(self, support, target, support_labels, real_support_labels, n_frames, way, merge_before,
                       single_direct):
@@ -329,12 +347,16 @@ class Engine:
         ep, S, Q = self._host_episode(support, target, support_labels, real_support_labels, n_frames, way,
                                       merge_before, single_direct)
         self._check(self.lib.fsar_episode_submit_host(self._h, slot, byref(ep)))
+        self._slot_refs[slot] = (support, target, support_labels, real_support_labels)
         return S, Q
 
     def episode_collect_host(self, slot, logits_out, class_logits_out=None):
-        self._check(self.lib.fsar_episode_collect_host(
-            self._h, slot, c_void_p(logits_out.data_ptr()),
-            c_void_p(class_logits_out.data_ptr()) if class_logits_out is not None else None))
+        try:
+            self._check(self.lib.fsar_episode_collect_host(
+                self._h, slot, c_void_p(logits_out.data_ptr()),
+                c_void_p(class_logits_out.data_ptr()) if class_logits_out is not None else None))
+        finally:
+            self._slot_refs.pop(slot, None)
 
     def episode_forward_host(self, support, target, support_labels, real_support_labels, n_frames, way,
                              merge_before=False, single_direct=False, n_train_classes=0):
@@ -380,11 +402,18 @@ class Engine:
                 if t.is_cuda or t.dtype != torch.uint8 or not t.is_contiguous() or tuple(t.shape[1:]) != (Hh, Ww, 3):
                     raise ValueError("%s must be a contiguous uint8 HOST tensor [frames, %d, %d, 3]" % (name, Hh, Ww))
             S, Q = sup.shape[0] // n_frames, tgt.shape[0] // n_frames
+            if S * n_frames != sup.shape[0] or Q * n_frames != tgt.shape[0]:
+                raise ValueError("frame counts %d / %d are not multiples of NUM_INPUT_FRAMES=%d" % (sup.shape[0], tgt.shape[0], n_frames))
+            for name, t in (("support_labels", sl), ("real_support_labels", rl)):
+                if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != S:
+                    raise ValueError("%s must be a contiguous fp32 HOST tensor with %d elements, got %s %s" %
+                                     (name, S, t.dtype, tuple(t.shape)))
             arr[i] = FsarEpisode(sup.data_ptr(), tgt.data_ptr(), sl.data_ptr(), rl.data_ptr(), S, Q, n_frames, way,
                                  int(bool(merge_before)), int(bool(single_direct)), 0, 0.9)
         F3 = c_float * 3
         self._check(self.lib.fsar_episodes_submit_host_u8(self._h, slot, arr, n, Hh, Ww, int(resize[0]), int(resize[1]),
                                                           F3(*(mean or self.CLIP_MEAN)), F3(*(std or self.CLIP_STD))))
+        self._slot_refs[slot] = list(episodes)
         return n, S, Q
 
     def metrics_update(self, logits, target_labels, counters, per_class=None):

@@ -64,7 +64,11 @@ class Synth_few_shot(torch.utils.data.Dataset):
         self.queries = int(getattr(cfg.TRAIN, "QUERY_PER_CLASS_TEST", None) or getattr(cfg.TRAIN, "QUERY_PER_CLASS", 1))
         self.frames = int(cfg.DATA.NUM_INPUT_FRAMES)
         self.size = int(getattr(cfg.DATA, "TEST_CROP_SIZE", 224))
-        self.n_cls = max(len(getattr(cfg.TEST, "CLASS_NAME", []) or []), self.way)
+        self.n_cls = len(getattr(cfg.TEST, "CLASS_NAME", []) or [])
+        if self.n_cls < self.way:
+            # real_support_labels index the rows of text_features_test (few_shot.py:2946), one per TEST.CLASS_NAME entry
+            raise ValueError("TEST.CLASS_NAME lists %d classes but the episodes are %d-way: real labels would index "
+                             "past text_features_test" % (self.n_cls, self.way))
         self.length = int(getattr(cfg.TRAIN, "NUM_TEST_TASKS", 100))
 
     def __len__(self):

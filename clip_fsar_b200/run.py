@@ -13,6 +13,9 @@ def main():
     root = os.environ.get("CLIP_FSAR_ROOT", "/root/reference")
     register(root)
     os.chdir(root)
+    # `python runs/run.py` puts runs/ at sys.path[0] (run.py does `from test import test`, `from train import train`);
+    # runpy.run_path does not, so do it here
+    sys.path.insert(0, os.path.join(root, "runs"))
     sys.argv[0] = os.path.join(root, "runs", "run.py")
     runpy.run_path(sys.argv[0], run_name="__main__")
 

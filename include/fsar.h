@@ -16,6 +16,11 @@
  *   - pointers named *_dev are device pointers, *_host are host pointers. All tensors are contiguous fp32
  *     unless stated otherwise. One handle per device, not thread-safe per handle.
  *   - there is no CPU fallback: every entry point fails with FSAR_E_CUDA when no sm_100 device is present.
+ *   - every entry point runs on the handle's device (cfg.device) and restores the caller's current device on return.
+ *   - input validation that needs device data (labels) happens on the device: kernels clamp every index they form from
+ *     caller labels and raise a flag in mapped host memory. *_collect_host reports it for the batch it collects
+ *     (FSAR_E_INVALID, after its event wait); the stream-ordered *_forward calls, which never synchronise, report it at
+ *     the NEXT call on the handle.
  */
 #ifndef FSAR_H_
 #define FSAR_H_
@@ -76,7 +81,7 @@ typedef struct fsar_episode {
     int32_t single_direct;             /* TRAIN.SINGLE_DIRECT (few_shot.py:2979) */
     int32_t text_mode;                 /* 0 = visual path (default); 1 = TRAIN.EVAL_TEXT (few_shot.py:2835-2852);
                                           2 = TRAIN.COMBINE (2855-2930). Modes 1/2 return class_logits = None in the
-                                          reference: class_logits_dev is left untouched. */
+                                          reference: the episode's slice of class_logits is zero-filled. */
     float text_coff;                   /* TRAIN.TEXT_COFF, exponent of the text probability in mode 2 (default 0.9) */
 } fsar_episode;
 
@@ -110,7 +115,10 @@ const char* fsar_last_error(const fsar_handle* h);
  *   "context2.layers.0.0.fn.to_q.weight", "scale",
  * plus the two non-state attributes "text_features_train" / "text_features_test" (few_shot.py:2720,2728;
  * numel / embed_dim rows). `data` holds `numel` fp32 values on the host (on_device == 0) or device.
- * GEMM weights are re-packed to the 16-bit tensor-core operand type inside the library. */
+ * GEMM weights are re-packed to the 16-bit tensor-core operand type inside the library.
+ * Ordering: fsar_set_weight is a synchronising call. It waits for all work in flight on the device (no forward may still
+ * be reading the weight), copies + re-packs, and waits again, so a forward enqueued afterwards on ANY stream sees the
+ * new value. `data` may be released as soon as the call returns. */
 int fsar_set_weight(fsar_handle* h, const char* name, const float* data, int64_t numel, int on_device);
 /* Number of weights that have not been set yet (0 => ready); names via fsar_missing_weight(i). */
 int fsar_missing_weights(const fsar_handle* h);
@@ -139,6 +147,11 @@ int fsar_episode_forward(fsar_handle* h, const fsar_episode* ep_dev, float* logi
  * [sum_i (n_support_i + n_target_i) * n_train_classes]. Same math per episode as fsar_episode_forward. */
 int fsar_episodes_forward(fsar_handle* h, const fsar_episode* eps_dev, int n_episodes, float* logits_dev,
                           float* class_logits_dev, void* stream);
+/* Host-buffer form of fsar_episodes_forward, pipelined over two slots (0 / 1): submit enqueues the host->device copies of
+ * the frames and labels on the library's copy stream, the compute and the device->host copy of the results, and returns
+ * WITHOUT waiting. Lifetime rule: every buffer an fsar_episode of the batch points to must stay allocated and unmodified
+ * until fsar_episodes_collect_host(slot) has returned (with pinned memory the copies are still in flight when submit
+ * returns). collect waits for the slot, reports label errors of that batch, and copies out the results. */
 int fsar_episodes_submit_host(fsar_handle* h, int slot, const fsar_episode* eps_host, int n_episodes);
 int fsar_episodes_collect_host(fsar_handle* h, int slot, float* logits_host, float* class_logits_host);
 
@@ -206,7 +219,7 @@ int fsar_op_layernorm(fsar_handle* h, const float* x_dev, const float* gamma_dev
 /* C[M,N] = A16[M,K] * W16[N,K]^T with epilogue epi (0 store16, 1 quickgelu16, 2 resid32 (out += ...), 4 store32). */
 int fsar_op_gemm(fsar_handle* h, const void* a16_dev, const void* w16_dev, const float* bias_dev, int M, int N, int K,
                  int epi, void* out_dev, void* stream);
-/* qkv16 [n_frames * L, 3 * D] -> out16 [n_frames * L, D], D = heads * 64 */
+/* qkv16 [n_frames * L, 3 * D] -> out16 [n_frames * L, D], D = heads * 64, L <= 257 (tcgen05 / TMEM attention core) */
 int fsar_op_attention(fsar_handle* h, const void* qkv16_dev, int n_frames, int L, int heads, void* out16_dev,
                       void* stream);
 int fsar_op_f32_to_16(fsar_handle* h, const float* src_dev, void* dst16_dev, int64_t numel, void* stream);
