@@ -410,7 +410,8 @@ int gemm(fsar_handle* h, int cls, const T16* a, const T16* w, const float* bias,
     RET_IF(get_tmap(h, a, M, K, GEMM_BM, GEMM_BK, 0, &ta, lda));
     RET_IF(get_tmap(h, w, N, K, pair ? GEMM2_BN / 2 : bn, GEMM_BK, 0, &tb));
     RET_IF(get_tmap(h, out, M, N, 32, out16 ? 64 : 32, out16 ? 0 : 1, &tc, ldc));
-    Scope s(h, st, cls, 2.0 * M * N * K, 0.0);
+    // algorithmic bytes: every unique tensor once (A, W, the output tile; the residual tile is the output itself)
+    Scope s(h, st, cls, 2.0 * M * N * K, 2.0 * ((double)M * K + (double)N * K) + (double)M * N * (out16 ? 2.0 : 4.0));
     if (pair) return launch_gemm_pair(h, epi, ta, tb, tc, p, st);
 #ifdef FSAR_PROBES
     if (bn == 256) return launch_gemm_bn<256>(h, epi, ta, tb, tc, p, st);   // FSAR_GEMM_SINGLE=1 A/B only

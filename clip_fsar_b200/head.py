@@ -242,7 +242,9 @@ class CNN_OTAM_CLIPFSAR_SM100(nn.Module):
             cap = max(n_videos, self._max_videos, 10)
             g = dict(self.geometry)
             n_cls = max(self.text_features_train.shape[0], self.text_features_test.shape[0], 1)
-            g.update(max_frames=min(cap * self.num_frames, 384), max_videos=cap, max_tokens=self.num_frames,
+            # one pass when the episode fits a wave of 256-row blocks (80 frames for 5-way 1-shot), else whole-wave passes
+            g.update(max_frames=min(cap * self.num_frames, _lib.best_pass_frames(g["image_size"], g["patch_size"])),
+                     max_videos=cap, max_tokens=self.num_frames,
                      max_classes=n_cls, otam_lambda=0.5, device=dev_index)
             self._engine = _lib.Engine(**g)
             self._pushed_versions = None

@@ -125,6 +125,14 @@ def load_library(path=None):
     return lib
 
 
+def best_pass_frames(image_size, patch_size, n_sm=148):
+    """Frames per ViT pass that make every GEMM a whole wave of 256-row blocks on the CTA pairs of one B200
+    (74 pairs x 256 rows / tokens per frame): 96 for ViT-B/16 (197 tokens), 73 for ViT-L/14 (257 tokens). Larger passes
+    only grow the activations past the 126 MB L2 (profiles/README.md, pass size sweep)."""
+    tokens = (image_size // patch_size) ** 2 + 1
+    return max(1, (n_sm // 2) * 256 // tokens)
+
+
 def geometry(backbone_name, num_frames=8, max_frames=None, max_videos=10, max_classes=128, mod_depth=1, device=0,
              max_batch=1):
     """fsar_config for the CLIP visual towers CNN_OTAM_CLIPFSAR can be built on (few_shot.py:2705-2713).
@@ -138,7 +146,8 @@ def geometry(backbone_name, num_frames=8, max_frames=None, max_videos=10, max_cl
         raise ValueError("unsupported VIDEO.HEAD.BACKBONE_NAME %r (supported: %s)" % (backbone_name, sorted(table)))
     g = dict(table[backbone_name])
     g.update(mod_heads=8, mod_dim_head=g["embed_dim"] // 8, mod_mlp_dim=2048, mod_depth=int(mod_depth),
-             max_frames=int(max_frames or min(max_videos * num_frames, 384)), max_videos=int(max_videos),
+             max_frames=int(max_frames or min(max_videos * num_frames, best_pass_frames(g["image_size"], g["patch_size"]))),
+             max_videos=int(max_videos),
              max_tokens=int(num_frames), max_classes=int(max_classes), max_batch=int(max_batch), otam_lambda=0.5,
              device=int(device))
     return g

@@ -32,13 +32,21 @@ def _stub(name, **kw):
         sys.modules[name] = m
 
 
+def _simplejson_dumps(obj, use_decimal=False, **kw):
+    """simplejson.dumps as utils/logging.py:86 calls it (sort_keys=True, use_decimal=True on a dict whose floats were
+    wrapped in decimal.Decimal): the stdlib encoder with Decimals written as plain numbers."""
+    import decimal
+    import json
+    return json.dumps(obj, default=lambda o: float(o) if isinstance(o, decimal.Decimal) else str(o), **kw)
+
+
 def stub_optional_dependencies():
     """Modules the reference imports at module scope but never needs on the few-shot inference path; absent in
     this image. Real installs are used when present."""
     _stub("ipdb", set_trace=lambda *a, **k: None)                      # few_shot.py:15
     _stub("ftfy", fix_text=lambda s: s)                                # few_shot.py:30
     _stub("oss2")                                                      # test_net_few_shot.py:12
-    _stub("simplejson", dumps=__import__("json").dumps, loads=__import__("json").loads)   # utils/logging.py:16
+    _stub("simplejson", dumps=_simplejson_dumps, loads=__import__("json").loads)          # utils/logging.py:16, 86
     if "decord" not in sys.modules:
         try:
             import decord  # noqa: F401

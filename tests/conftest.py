@@ -17,8 +17,10 @@ def pytest_configure(config):
 
 
 def golden_names():
-    """Episode fixtures (preproc_* belong to tests/test_preprocess.py, text_* to tests/test_text_tower.py)."""
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith(("preproc_", "text_")))
+    """Episode fixtures (preproc_* belong to tests/test_preprocess.py, text_* to tests/test_text_tower.py, the full-depth
+    ViT-L/14 episode has tests of its own)."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR)
+                  if f.endswith(".npz") and not f.startswith(("preproc_", "text_", "vitl14_")))
 
 
 def load_golden(name):

@@ -3,7 +3,9 @@
 
 Tolerances. The CUDA path stores GEMM operands in fp16 (fp32 accumulation, fp32 residual stream / LN / softmax
 statistics, fp32 head); the reference is fp32 end to end. north_star's bound is 1e-3 relative on the logits:
-  * default-init ViT-B/16 (the configuration BASELINE.json names): max|dlogit| / max|logit| <= 1e-3;
+  * default-init weights (the configuration BASELINE.json names) -- EVERY flag variant has a `*_di` / `*_default_init`
+    fixture produced by the reference: max|dlogit| / max|logit| <= 1e-3, AND the same bound on the row-centred logits
+    (l - rowmean(l)), which removes the T-proportional soft-min offset that inflates max|logit| (SURVEY.md 7.3-2b);
   * "spread" weights (sharpened attention, perturbed LN affine terms, see synth.py) are a deliberately harder
     stress case where fp16 operand rounding ALONE (oracle with operand_dtype=fp16, no GPU involved) already gives
     ~1.4e-3, so the bound there is 3e-3 on logits / 5e-3 rel-L2 on features, plus a TIGHT bound against the
@@ -27,6 +29,14 @@ def rel_l2(a, b):
 def rel_max(a, b):
     a, b = torch.as_tensor(a).float().cpu(), torch.as_tensor(b).float().cpu()
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def rel_centred(a, b):
+    """max |(a - rowmean(a)) - (b - rowmean(b))| / max|b|: the additive OTAM offset (proportional to T, doubled by the
+    bidirectional sum) carries no class information; this is the error on what the argmax actually sees."""
+    a, b = torch.as_tensor(a).float().cpu(), torch.as_tensor(b).float().cpu()
+    ac, bc = a - a.mean(dim=1, keepdim=True), b - b.mean(dim=1, keepdim=True)
+    return float((ac - bc).abs().max() / (b.abs().max() + 1e-30))
 
 
 def make_engine(lib, meta, g, sd, tt, te, max_frames=None):
@@ -68,10 +78,15 @@ def test_episode_matches_reference_fixture(lib, name):
     if mode != 1 and not slim:
         assert float(np.abs(e.peek("dists", (Q, way, T, T)).numpy() - ref["dists"]).max()) < 3e-3
     assert rel_max(logits, ref["logits"]) < tol_logits
+    assert rel_centred(logits, ref["logits"]) < tol_logits
     assert logits.shape == ref["logits"].shape
     if mode == 0:
         assert rel_max(class_logits, ref["class_logits"]) < 3e-3 and class_logits.shape == ref["class_logits"].shape
-        assert (logits.cpu().numpy().argmax(1) == ref["logits"].argmax(1)).all()
+        # argmax wherever the reference's own top-2 margin is above the stated tolerance (random-init rows can be tied
+        # to 1e-4 of the logit scale; a tie is not a parity failure)
+        top2 = np.sort(ref["logits"], axis=1)[:, -2:]
+        sure = (top2[:, 1] - top2[:, 0]) > 2 * tol_logits * np.abs(ref["logits"]).max()
+        assert (logits.cpu().numpy().argmax(1)[sure] == ref["logits"].argmax(1)[sure]).all()
     else:
         # text branches return probabilities (rows sum to ... <= 1) and class_logits = None (few_shot.py:2852, 2930);
         # the argmax is only compared where the reference's top-2 margin exceeds the 16-bit noise
@@ -95,6 +110,30 @@ def test_episode_matches_16bit_emulating_oracle_tightly(lib, name):
     assert rel_l2(e.peek("support_feats", (S, T, E)), out["support_feats"]) < 1.5e-3      # tanh.approx vs torch.tanh
     assert rel_max(logits, out["logits"]) < 1e-3
     assert torch.equal(e.peek("class_index", (S,), torch.int32).long(), out["class_index"])
+    e.close()
+
+
+def test_vitl14_full_depth_16_frame_episode(lib):
+    """BASELINE.json configs[3]: ViT-L/14 (24 layers, 257 tokens, width 1024), 5-way 1-shot, 16 frames = 160 frames, the
+    WHOLE episode (modulator 8 x 96, OTAM 16 x 16) against (a) the fixture the reference's own classes produced and
+    (b) the fp16-operand-emulating oracle's outputs stored in the same fixture (twice the depth of ViT-B/16: rounding
+    accumulates over 24 blocks)."""
+    meta, ref = load_golden("vitl14_5w1s_T16_default_init")
+    g, sd, tt, te, task = regenerate(meta)
+    assert g["layers"] == 24 and g["width"] == 1024
+    e = make_engine(lib, meta, g, sd, tt, te, max_frames=80)      # two 80-frame passes
+    logits, class_logits = run(e, meta, task)
+    S, Q, T, E, way = 5, 5, 16, g["embed_dim"], 5
+    sf, tf = e.peek("support_feats", (S, T, E)), e.peek("target_feats", (Q, T, E))
+    assert rel_l2(sf, ref["support_feats"]) < 5e-3 and rel_l2(tf, ref["target_feats"]) < 5e-3
+    assert rel_l2(sf, ref["emu16_support_feats"]) < 2e-3 and rel_l2(tf, ref["emu16_target_feats"]) < 2e-3
+    assert float(np.abs(e.peek("dists", (Q, way, T, T)).numpy() - ref["dists"]).max()) < 3e-3
+    assert rel_max(logits, ref["logits"]) < 1e-3 and rel_centred(logits, ref["logits"]) < 1e-3
+    assert rel_max(logits, ref["emu16_logits"]) < 1e-3
+    assert rel_max(class_logits, ref["class_logits"]) < 3e-3
+    top2 = np.sort(ref["logits"], axis=1)[:, -2:]
+    sure = (top2[:, 1] - top2[:, 0]) > 2e-3 * np.abs(ref["logits"]).max()
+    assert (logits.cpu().numpy().argmax(1)[sure] == ref["logits"].argmax(1)[sure]).all()
     e.close()
 
 

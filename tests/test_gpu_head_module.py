@@ -1,6 +1,7 @@
 """GPU: the registered nn.Module (the drop-in boundary) drives the same C-ABI path and agrees with the fixtures."""
 import types
 
+import numpy as np
 import pytest
 import torch
 
@@ -14,7 +15,12 @@ pytestmark = pytest.mark.gpu
                                         ("tiny_3w2s_T32_single", {"SINGLE_DIRECT": True}),
                                         ("tiny_5w1s_depth2", {"TRANSFORMER_DEPTH": 2}),
                                         ("tiny_5w5s_evaltext", {"EVAL_TEXT": True}),
-                                        ("tiny_5w5s_combine_coff05_merge", {"COMBINE": True, "TEXT_COFF": 0.5, "MERGE_BEFORE": True})])
+                                        ("tiny_5w5s_combine_coff05_merge", {"COMBINE": True, "TEXT_COFF": 0.5, "MERGE_BEFORE": True}),
+                                        # default-init weights: north_star's 1e-3 bound through the registered module
+                                        ("tiny_5w1s_default_init", {}), ("tiny_5w5s_merge_di", {"MERGE_BEFORE": True}),
+                                        ("tiny_3w2s_T32_single_di", {"SINGLE_DIRECT": True}),
+                                        ("tiny_5w1s_depth2_di", {"TRANSFORMER_DEPTH": 2}),
+                                        ("tiny_5w1s_combine_di", {"COMBINE": True})])
 def test_module_forward_matches_reference_fixture(name, flags):
     from clip_fsar_b200.head import CNN_OTAM_CLIPFSAR_SM100
     meta, ref = load_golden(name)
@@ -28,9 +34,11 @@ def test_module_forward_matches_reference_fixture(name, flags):
     assert set(out) == {"logits", "class_logits"}
     assert out["logits"].is_cuda and out["logits"].shape == ref["logits"].shape
     err = (out["logits"].cpu() - torch.from_numpy(ref["logits"])).abs().max() / abs(ref["logits"]).max()
-    assert float(err) < 3e-3
+    assert float(err) < (3e-3 if meta["spread"] else 1e-3)
     if not (flags.get("EVAL_TEXT") or flags.get("COMBINE")):
-        assert (out["logits"].cpu().numpy().argmax(1) == ref["logits"].argmax(1)).all()
+        top2 = np.sort(ref["logits"], axis=1)[:, -2:]
+        sure = (top2[:, 1] - top2[:, 0]) > 2e-3 * abs(ref["logits"]).max()
+        assert (out["logits"].cpu().numpy().argmax(1)[sure] == ref["logits"].argmax(1)[sure]).all()
     else:
         assert out["class_logits"] is None          # few_shot.py:2852 / 2930
         return

@@ -6,7 +6,7 @@ import torch
 from conftest import golden_names, load_golden, regenerate
 from oracle import fsar_oracle as O
 
-FAST = [n for n in golden_names() if not n.startswith("vitb16")]
+FAST = [n for n in golden_names() if not n.startswith(("vitb16", "vitl14"))]
 FULL = [n for n in golden_names() if n.startswith("vitb16")]
 
 
@@ -38,6 +38,23 @@ def test_oracle_matches_reference_outputs(name):
     else:                                       # the reference returns class_logits = None in the text branches
         assert out["class_logits"] is None and ref["class_logits"].size == 0
     assert (out["logits"].numpy().argmax(1) == ref["logits"].argmax(1)).all()
+
+
+def test_vitl14_full_depth_fixture_is_consistent():
+    """The 24-layer ViT-L/14 episode takes minutes on CPU, so it is not recomputed here: the fixture holds the
+    reference's outputs AND the fp16-emulating oracle's (oracle/gen_golden.py, emu16). Regenerated inputs must be the
+    ones the reference saw, and 16-bit operand rounding alone must stay inside north_star's 1e-3."""
+    meta, ref = load_golden("vitl14_5w1s_T16_default_init")
+    g, sd, tt, te, task = regenerate(meta)
+    assert g["layers"] == 24 and task["support_set"].shape == (80, 3, 224, 224)
+    assert np.isclose(sum(np.float64(v).sum() for v in sd.values()), ref["weight_checksum"][0], rtol=0, atol=1e-6)
+    assert np.isclose(np.float64(task["support_set"]).sum() + np.float64(task["target_set"]).sum(),
+                      ref["input_checksum"][0], rtol=0, atol=1e-6)
+    assert rel(ref["emu16_logits"], ref["logits"]) < 1e-3
+    # the head alone (modulator 8 x 96 heads, OTAM 16 x 16) recomputed from the reference's frame features
+    out = O.head_forward(sd, g, tt, te, torch.from_numpy(ref["support_feats"]), torch.from_numpy(ref["target_feats"]),
+                         task["support_labels"], task["real_support_labels"])
+    assert rel(out["logits"], ref["logits"]) < 1e-5 and rel(out["dists"], ref["dists"]) < 1e-5
 
 
 def test_state_dict_names_match_reference():
