@@ -142,6 +142,9 @@ struct fsar_handle {
     EncodeFn encode = nullptr;
     std::map<std::tuple<const void*, int, int, int, long long>, CUtensorMap> tmaps;
     std::set<const void*> smem_opt_in;   // kernels whose dynamic smem limit has been raised on this handle's device
+    // non-null while a uint8 entry point is enqueueing: the frame pointers of the segments address RAW uint8 [H, W, 3]
+    // frames of this geometry, and the patch gather does the resize / crop / normalise itself (8f-1)
+    const PreprocParams* u8_src = nullptr;
     // ---- host-buffer path
     HostSlot slot[2];
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
@@ -820,6 +823,16 @@ int vit_encode_gathered(fsar_handle* h, int n, float* feats_out, cudaStream_t st
 int patch_gather(fsar_handle* h, const float* frames, int n, int row_frame_offset, cudaStream_t st) {
     const fsar_config& c = h->cfg;
     const int S = c.image_size, P = c.patch_size, G = h->grid;
+    if (h->u8_src != nullptr) {
+        PreprocParams pp = *h->u8_src;
+        pp.n = n;
+        const long long total = (long long)n * S * (S / 2);
+        Scope s(h, st, FSAR_K_PATCH_GATHER, 0.0, (double)n * (3.0 * pp.H * pp.W + 6.0 * S * S));
+        launch_pdl(h, preprocess_patches_u8_kernel<T16>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st,
+                   reinterpret_cast<const uint8_t*>(frames), h->patches16 + (size_t)row_frame_offset * G * G * h->patch_kp, pp,
+                   P, h->patch_kp);
+        return check_launch(h, "preprocess_patches_u8_kernel");
+    }
     const long long total = (long long)n * 3 * S * G;
     const int grid = (int)((total + 255) / 256);
     Scope s(h, st, FSAR_K_PATCH_GATHER, 0.0, (double)n * 3 * S * S * 6.0);
@@ -833,7 +846,9 @@ int patch_gather(fsar_handle* h, const float* frames, int n, int row_frame_offse
 int vit_encode_segments(fsar_handle* h, const float* const* ptrs, const int* counts, int nseg, float* feats,
                         cudaStream_t st) {
     const fsar_config& c = h->cfg;
-    const size_t frame_elems = (size_t)3 * c.image_size * c.image_size;
+    // distance between consecutive frames of a segment in units of float (the pointer type): fp32 crops, or raw uint8
+    // frames addressed through the same pointers (u8_src; H * W * 3 bytes is a multiple of 4 only by luck, so step in bytes)
+    const size_t frame_bytes = h->u8_src ? (size_t)h->u8_src->H * h->u8_src->W * 3 : sizeof(float) * 3 * c.image_size * c.image_size;
     int total = 0;
     for (int i = 0; i < nseg; ++i) total += counts[i];
     int seg = 0, seg_off = 0, done = 0;
@@ -844,7 +859,8 @@ int vit_encode_segments(fsar_handle* h, const float* const* ptrs, const int* cou
             while (seg_off == counts[seg]) { ++seg; seg_off = 0; }
             const int avail = counts[seg] - seg_off;
             const int take = (avail < n - filled) ? avail : n - filled;
-            RET_IF(patch_gather(h, ptrs[seg] + (size_t)seg_off * frame_elems, take, filled, st));
+            RET_IF(patch_gather(h, reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(ptrs[seg]) + (size_t)seg_off * frame_bytes),
+                                take, filled, st));
             filled += take;
             seg_off += take;
         }
@@ -1348,14 +1364,23 @@ int fsar_episode_forward_host(fsar_handle* h, const fsar_episode* ep, float* log
     return fsar_episodes_collect_host(h, 0, logits_host, class_logits_host);
 }
 
-static int preprocess_u8(fsar_handle* h, const uint8_t* src, int n, int H, int W, int rh, int rw, const float* mean,
-                         const float* std, float* dst, cudaStream_t st) {
+static int preproc_params(fsar_handle* h, int n, int H, int W, int rh, int rw, const float* mean, const float* std,
+                          PreprocParams* out) {
     const int S = h->cfg.image_size;
     if (n < 1 || H < 1 || W < 1 || rh < S || rw < S || mean == nullptr || std == nullptr)
         return fail(h, FSAR_E_INVALID, "preprocess: bad geometry (n %d, source %dx%d, resize %dx%d, crop %d)", n, H, W, rh, rw, S);
     PreprocParams pp;
     pp.n = n; pp.H = H; pp.W = W; pp.RH = rh; pp.RW = rw; pp.S = S;
     for (int c = 0; c < 3; ++c) { pp.mean[c] = mean[c]; pp.std[c] = std[c]; }
+    *out = pp;
+    return 0;
+}
+
+static int preprocess_u8(fsar_handle* h, const uint8_t* src, int n, int H, int W, int rh, int rw, const float* mean,
+                         const float* std, float* dst, cudaStream_t st) {
+    const int S = h->cfg.image_size;
+    PreprocParams pp;
+    RET_IF(preproc_params(h, n, H, W, rh, rw, mean, std, &pp));
     const long long total = (long long)n * S * S;
     Scope s(h, st, FSAR_K_PATCH_GATHER, 0.0, (double)n * (3.0 * H * W + 12.0 * S * S));
     preprocess_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, dst, pp);
@@ -1369,6 +1394,21 @@ int fsar_preprocess_u8(fsar_handle* h, const uint8_t* frames_u8_dev, int n_frame
     return preprocess_u8(h, frames_u8_dev, n_frames, H, W, resize_h, resize_w, mean, std, out_dev, (cudaStream_t)stream);
 }
 
+int fsar_vit_forward_u8(fsar_handle* h, const uint8_t* frames_u8_dev, int n_frames, int H, int W, int resize_h, int resize_w,
+                        const float mean[3], const float std[3], float* feats_dev, void* stream) {
+    DeviceGuard guard(h);
+    if (h == nullptr || frames_u8_dev == nullptr || feats_dev == nullptr || n_frames < 1)
+        return fail(h, FSAR_E_INVALID, "fsar_vit_forward_u8: bad argument");
+    if (!ready(h, false)) return fail(h, FSAR_E_STATE, "%d weights have not been set (first: %s)", fsar_missing_weights(h), fsar_missing_weight(h, 0));
+    PreprocParams pp;
+    RET_IF(preproc_params(h, n_frames, H, W, resize_h, resize_w, mean, std, &pp));
+    const float* ptr = reinterpret_cast<const float*>(frames_u8_dev);
+    h->u8_src = &pp;
+    const int rc = vit_encode_segments(h, &ptr, &n_frames, 1, feats_dev, (cudaStream_t)stream);
+    h->u8_src = nullptr;
+    return rc;
+}
+
 int fsar_episodes_submit_host_u8(fsar_handle* h, int slot, const fsar_episode* eps, int n_episodes, int H, int W,
                                  int resize_h, int resize_w, const float mean[3], const float std[3]) {
     DeviceGuard guard(h);
@@ -1378,7 +1418,9 @@ int fsar_episodes_submit_host_u8(fsar_handle* h, int slot, const fsar_episode* e
     HostSlot& s = h->slot[slot];
     if (s.busy) return fail(h, FSAR_E_STATE, "slot %d still holds uncollected episodes", slot);
     const fsar_config& c = h->cfg;
-    const size_t frame_elems = (size_t)3 * c.image_size * c.image_size, raw_frame = (size_t)H * W * 3;
+    const size_t raw_frame = (size_t)H * W * 3;
+    PreprocParams pp;
+    RET_IF(preproc_params(h, 1, H, W, resize_h, resize_w, mean, std, &pp));
     size_t total_frames = 0;
     for (int i = 0; i < n_episodes; ++i) total_frames += (size_t)(eps[i].n_support + eps[i].n_target) * eps[i].n_frames;
     if (total_frames * raw_frame > s.raw_bytes) {
@@ -1396,8 +1438,9 @@ int fsar_episodes_submit_host_u8(fsar_handle* h, int slot, const fsar_episode* e
         CU_OK(h, cudaMemcpyAsync(s.raw_dev + (f_off + ns) * raw_frame, ep.target_frames, nt * raw_frame, cudaMemcpyHostToDevice, h->copy_stream));
         CU_OK(h, cudaMemcpyAsync(lab, ep.support_labels, sizeof(float) * ep.n_support, cudaMemcpyHostToDevice, h->copy_stream));
         CU_OK(h, cudaMemcpyAsync(lab + c.max_videos, ep.real_support_labels, sizeof(float) * ep.n_support, cudaMemcpyHostToDevice, h->copy_stream));
-        dev[i].support_frames = s.frames_dev + f_off * frame_elems;
-        dev[i].target_frames = s.frames_dev + (f_off + ns) * frame_elems;
+        // the episode's frame pointers address the RAW bytes: the patch gather resizes / crops / normalises (u8_src)
+        dev[i].support_frames = reinterpret_cast<const float*>(s.raw_dev + f_off * raw_frame);
+        dev[i].target_frames = reinterpret_cast<const float*>(s.raw_dev + (f_off + ns) * raw_frame);
         dev[i].support_labels = lab;
         dev[i].real_support_labels = lab + c.max_videos;
         f_off += ns + nt;
@@ -1406,8 +1449,10 @@ int fsar_episodes_submit_host_u8(fsar_handle* h, int slot, const fsar_episode* e
     }
     CU_OK(h, cudaEventRecord(s.copied, h->copy_stream));
     CU_OK(h, cudaStreamWaitEvent(h->compute_stream, s.copied, 0));
-    RET_IF(preprocess_u8(h, s.raw_dev, (int)total_frames, H, W, resize_h, resize_w, mean, std, s.frames_dev, h->compute_stream));
-    RET_IF(episodes_forward_dev(h, dev.data(), n_episodes, s.logits_dev, s.clogits_dev, h->compute_stream));
+    h->u8_src = &pp;
+    const int rc = episodes_forward_dev(h, dev.data(), n_episodes, s.logits_dev, s.clogits_dev, h->compute_stream);
+    h->u8_src = nullptr;
+    RET_IF(rc);
     CU_OK(h, cudaMemcpyAsync(s.logits_pin, s.logits_dev, sizeof(float) * n_logits, cudaMemcpyDeviceToHost, h->compute_stream));
     CU_OK(h, cudaMemcpyAsync(s.clogits_pin, s.clogits_dev, sizeof(float) * n_clogits, cudaMemcpyDeviceToHost, h->compute_stream));
     CU_OK(h, cudaEventRecord(s.done, h->compute_stream));

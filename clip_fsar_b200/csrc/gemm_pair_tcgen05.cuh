@@ -164,7 +164,7 @@ gemm_tn_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
             tc_fence_after();
             const uint32_t t_base = tmem_base + acc * BN + (uint32_t(q * 32) << 16);
             const uint32_t leader_tempty = map_to_cta(smem_u32(&tempty_bar[acc]), 0);
-            gemm_epilogue_tile<BN, EPI, T16>(t_base, row0, n_blk * BN, p, &tmC, stage_ptr, row_addr, sw, half, lane,
+            gemm_epilogue_tile<BN, EPI, T16>(t_base, row0, n_blk * BN, p, &tmC, stage_ptr, row_addr, sw, half, 2, lane,
                                              [&]() { mbar_arrive_cluster(leader_tempty); });
             if (++acc == 2) {
                 acc = 0;

@@ -114,12 +114,13 @@ __device__ __forceinline__ uint32_t quick_gelu_pack2<__nv_bfloat16>(float a, flo
 }
 
 // Epilogue of one 128-row x BN-column accumulator tile for ONE warp: lanes [32 q, 32 q + 32) of TMEM (t_base already
-// points at them), the column chunks of parity `half`. tcgen05.ld -> fused tail -> 128B-swizzled smem staging tile ->
+// points at them), the column chunks c_first, c_first + c_step, ... (two warps per lane quarter take the chunks of even /
+// odd index: (half, 2); one warp takes them all: (0, 1)). tcgen05.ld -> fused tail -> 128B-swizzled smem staging tile ->
 // TMA store / reduce-add. `release()` hands the accumulator back to the MMA warp as soon as this warp has read its share.
 template <int BN, int EPI, typename T16, typename Release>
 __device__ __forceinline__ void gemm_epilogue_tile(uint32_t t_base, int row0, int col_base, const GemmParams& p,
                                                    const CUtensorMap* tmC, uint8_t* stage_ptr, uint32_t row_addr,
-                                                   uint32_t sw, int half, int lane, Release release) {
+                                                   uint32_t sw, int c_first, int c_step, int lane, Release release) {
     constexpr bool kOut16 = (EPI == EPI_STORE16 || EPI == EPI_QGELU16);
     constexpr int CHUNK = kOut16 ? 64 : 32;
     constexpr int NCH = BN / CHUNK;
@@ -132,7 +133,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(uint32_t t_base, int row0, in
     }
 
 #pragma unroll 1
-    for (int c = half; c < NCH; c += 2) {
+    for (int c = c_first; c < NCH; c += c_step) {
         const int col0 = col_base + c * CHUNK;
         uint32_t w[32];  // the staging row of this thread: 128 B
         if (kOut16) {
@@ -140,7 +141,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(uint32_t t_base, int row0, in
             tmem_ld_32x32b_x32(t_base + c * 64, r0);
             tmem_ld_32x32b_x32(t_base + c * 64 + 32, r1);
             tc_wait_ld();
-            if (c + 2 >= NCH) {  // this warp's share of the accumulator is read: hand it back early
+            if (c + c_step >= NCH) {  // this warp's share of the accumulator is read: hand it back early
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) release();
@@ -172,7 +173,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(uint32_t t_base, int row0, in
         } else {
             tmem_ld_32x32b_x32(t_base + c * 32, w);
             tc_wait_ld();
-            if (c + 2 >= NCH) {
+            if (c + c_step >= NCH) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) release();
@@ -355,7 +356,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_base = tmem_base + acc * BN + (uint32_t(q * 32) << 16);
-            gemm_epilogue_tile<BN, EPI, T16>(t_base, row0, n_blk * BN, p, &tmC, stage_ptr, row_addr, sw, half, lane,
+            gemm_epilogue_tile<BN, EPI, T16>(t_base, row0, n_blk * BN, p, &tmC, stage_ptr, row_addr, sw, half, 2, lane,
                                              [&]() { mbar_arrive(&tempty_bar[acc]); });
             if (++acc == 2) {
                 acc = 0;

@@ -54,6 +54,61 @@ preprocess_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, c
     }
 }
 
+// The same transform fused INTO the patch gather ("feeding K1 directly"): uint8 [n, H, W, 3] -> the
+// 16-bit im2col rows [n * G * G, Kp] of the conv1 GEMM, k = c * P * P + ky * P + kx. The fp32 NCHW crop (48 MB per
+// 80-frame episode, written once and read once) never exists. Arithmetic is preprocess_u8_kernel's, rounded to the operand
+// type exactly as patch_gather_kernel rounds the fp32 crop, so both routes give bit-identical patch rows.
+// One thread per (frame, y, pair of x): two horizontally adjacent pixels x 3 channels, three 4-byte stores.
+template <typename T16>
+__global__ void __launch_bounds__(256)
+preprocess_patches_u8_kernel(const uint8_t* __restrict__ src, T16* __restrict__ out, const PreprocParams p, int P, int Kp) {
+    pdl_trigger();
+    pdl_wait();
+    const int half_w = p.S >> 1;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)p.n * p.S * half_w;
+    if (idx >= total) return;
+    const int x0 = int(idx % half_w) * 2;
+    const int y = int((idx / half_w) % p.S);
+    const int f = int(idx / ((long long)half_w * p.S));
+    const int G = p.S / P;
+    const float sh = float(p.H) / float(p.RH), sw = float(p.W) / float(p.RW);
+    const int ry = y + (p.RH - p.S) / 2;
+    float fy = sh * (float(ry) + 0.5f) - 0.5f;
+    fy = fy < 0.f ? 0.f : fy;
+    const int sy0 = int(fy);
+    const int sy1 = sy0 + (sy0 < p.H - 1 ? 1 : 0);
+    const float ly1 = fy - float(sy0), ly0 = 1.0f - ly1;
+    const uint8_t* base = src + (size_t)f * p.H * p.W * 3;
+    float v[2][3];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int rx = x0 + i + (p.RW - p.S) / 2;
+        float fx = sw * (float(rx) + 0.5f) - 0.5f;
+        fx = fx < 0.f ? 0.f : fx;
+        const int sx0 = int(fx);
+        const int sx1 = sx0 + (sx0 < p.W - 1 ? 1 : 0);
+        const float lx1 = fx - float(sx0), lx0 = 1.0f - lx1;
+        const uint8_t* p00 = base + ((size_t)sy0 * p.W + sx0) * 3;
+        const uint8_t* p01 = base + ((size_t)sy0 * p.W + sx1) * 3;
+        const uint8_t* p10 = base + ((size_t)sy1 * p.W + sx0) * 3;
+        const uint8_t* p11 = base + ((size_t)sy1 * p.W + sx1) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v00 = float(p00[c]) / 255.0f, v01 = float(p01[c]) / 255.0f;
+            const float v10 = float(p10[c]) / 255.0f, v11 = float(p11[c]) / 255.0f;
+            const float t = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+            v[i][c] = (t - p.mean[c]) / p.std[c];
+        }
+    }
+    const int py = y / P, ky = y - py * P;
+    const int px = x0 / P, kx = x0 - px * P;       // P is even: both pixels fall into the same patch
+    T16* dst = out + ((size_t)f * G * G + (size_t)py * G + px) * Kp + (size_t)ky * P + kx;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        *reinterpret_cast<uint32_t*>(dst + (size_t)c * P * P) = pack2<T16>(v[0][c], v[1][c]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Patch gather: frames NCHW fp32 [n, 3, S, S] -> A16 [n * G * G, Kp], k = c * P * P + ky * P + kx
 // (the flattening of conv1.weight [width, 3, P, P], few_shot.py:659,672). One thread per (frame, c, y, px):

@@ -23,7 +23,7 @@ SYMBOLS = [
     "fsar_missing_weights", "fsar_missing_weight", "fsar_vit_forward", "fsar_modulate", "fsar_otam_logits",
     "fsar_episode_forward", "fsar_episode_forward_host", "fsar_episode_submit_host", "fsar_episode_collect_host",
     "fsar_episodes_forward", "fsar_episodes_submit_host", "fsar_episodes_collect_host",
-    "fsar_preprocess_u8", "fsar_episodes_submit_host_u8", "fsar_text_configure", "fsar_text_encode", "fsar_metrics_update", "fsar_peek", "fsar_operand_dtype", "fsar_op_layernorm", "fsar_op_gemm", "fsar_op_attention", "fsar_op_f32_to_16",
+    "fsar_preprocess_u8", "fsar_vit_forward_u8", "fsar_episodes_submit_host_u8", "fsar_text_configure", "fsar_text_encode", "fsar_metrics_update", "fsar_peek", "fsar_operand_dtype", "fsar_op_layernorm", "fsar_op_gemm", "fsar_op_attention", "fsar_op_f32_to_16",
     "fsar_launch_count", "fsar_profile_begin", "fsar_profile_end",
 ]
 
@@ -105,6 +105,7 @@ def load_library(path=None):
     lib.fsar_episodes_collect_host.argtypes = [H, c_int, c_void_p, c_void_p]
     F3 = c_float * 3
     lib.fsar_preprocess_u8.argtypes = [H, c_void_p, c_int, c_int, c_int, c_int, c_int, F3, F3, c_void_p, c_void_p]
+    lib.fsar_vit_forward_u8.argtypes = [H, c_void_p, c_int, c_int, c_int, c_int, c_int, F3, F3, c_void_p, c_void_p]
     lib.fsar_episodes_submit_host_u8.argtypes = [H, c_int, POINTER(FsarEpisode), c_int, c_int, c_int, c_int, c_int, F3, F3]
     lib.fsar_text_configure.argtypes = [H, POINTER(FsarTextConfig)]
     lib.fsar_text_encode.argtypes = [H, c_void_p, c_int, c_void_p, c_void_p]
@@ -396,6 +397,21 @@ class Engine:
         self._check(self.lib.fsar_preprocess_u8(self._h, c_void_p(frames_u8.data_ptr()), n, Hh, Ww, int(resize[0]),
                                                 int(resize[1]), F3(*(mean or self.CLIP_MEAN)), F3(*(std or self.CLIP_STD)),
                                                 c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def vit_forward_u8(self, frames_u8, resize=(256, 256), mean=None, std=None):
+        """uint8 [n, H, W, 3] CUDA -> frame features [n, embed_dim]; resize / crop / normalise happen inside the patch
+        gather (no fp32 crop in HBM). Same numbers as vit_forward(preprocess_u8(frames_u8))."""
+        torch = self._torch
+        if not (frames_u8.is_cuda and frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous() and frames_u8.dim() == 4
+                and frames_u8.shape[3] == 3):
+            raise ValueError("frames_u8 must be a contiguous uint8 CUDA tensor [n, H, W, 3]")
+        n, Hh, Ww, _ = frames_u8.shape
+        out = torch.empty((n, self.cfg.embed_dim), dtype=torch.float32, device=self.device)
+        F3 = c_float * 3
+        self._check(self.lib.fsar_vit_forward_u8(self._h, c_void_p(frames_u8.data_ptr()), n, Hh, Ww, int(resize[0]),
+                                                 int(resize[1]), F3(*(mean or self.CLIP_MEAN)), F3(*(std or self.CLIP_STD)),
+                                                 c_void_p(out.data_ptr()), self._stream()))
         return out
 
     def episodes_submit_host_u8(self, slot, episodes, n_frames, way, resize=(256, 256), mean=None, std=None,

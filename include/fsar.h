@@ -171,9 +171,15 @@ int fsar_episode_collect_host(fsar_handle* h, int slot, float* logits_host, floa
  * frames_u8_dev uint8 [n_frames, H, W, 3] -> out_dev fp32 [n_frames, 3, image_size, image_size] (task-dict layout). */
 int fsar_preprocess_u8(fsar_handle* h, const uint8_t* frames_u8_dev, int n_frames, int H, int W, int resize_h, int resize_w,
                        const float mean[3], const float std[3], float* out_dev, void* stream);
+/* VisionTransformer.forward on RAW frames: the transform above is evaluated inside the patch gather (uint8 [H, W, 3] ->
+ * 16-bit im2col rows of conv1), the fp32 [n, 3, S, S] crop is never materialised. Bit-identical to
+ * fsar_preprocess_u8 followed by fsar_vit_forward. */
+int fsar_vit_forward_u8(fsar_handle* h, const uint8_t* frames_u8_dev, int n_frames, int H, int W, int resize_h, int resize_w,
+                        const float mean[3], const float std[3], float* feats_dev, void* stream);
 /* fsar_episodes_submit_host with RAW uint8 frames: support_frames / target_frames of each episode point to HOST uint8
- * [videos * n_frames, H, W, 3]; the bytes are copied as they are and pre-processed on the device (4x less H2D traffic
- * than fp32 crops at 224 x 224 sources). Collect with fsar_episodes_collect_host. */
+ * [videos * n_frames, H, W, 3]; the bytes are copied as they are and pre-processed on the device inside the patch gather
+ * (4x less H2D traffic than fp32 crops at 224 x 224 sources, no fp32 intermediate in HBM). Collect with
+ * fsar_episodes_collect_host; the lifetime rule of fsar_episodes_submit_host applies. */
 int fsar_episodes_submit_host_u8(fsar_handle* h, int slot, const fsar_episode* eps_host_u8, int n_episodes, int H, int W,
                                  int resize_h, int resize_w, const float mean[3], const float std[3]);
 

@@ -45,7 +45,10 @@ def test_layernorm_rejects_unsupported_dim(eng, lib):
 
 
 GEMM_SHAPES = [(128, 256, 64), (1, 64, 64), (127, 72, 136), (300, 256, 192), (1000, 768, 768), (1000, 2304, 768),
-               (777, 768, 3072), (333, 128, 64), (1970, 3072, 768), (15760, 768, 768)]
+               (777, 768, 3072), (333, 128, 64), (1970, 3072, 768), (15760, 768, 768),
+               # exactly two tile columns, ragged last column blocks (1280 = 5 x 256; 1096 is not a multiple of 64), and the
+               # full 96-frame QKV shape
+               (600, 512, 128), (300, 1280, 192), (515, 1096, 72), (18912, 2304, 768)]
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)

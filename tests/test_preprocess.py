@@ -77,3 +77,25 @@ def test_uint8_host_entry_point_equals_float_path(lib):
     # the crops agree to ~1e-6; a few of those flip a 16-bit operand rounding in the ViT, hence not bit equal
     assert float((got - want.cpu()).abs().max() / want.abs().max()) < 1e-3
     e.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom,H,W,scale", [("tiny", 48, 64, 40), ("ViT-B/16", 240, 320, 256), ("ViT-B/16", 128, 171, 256),
+                                            ("l14-2layer", 360, 640, 256)])
+def test_fused_u8_patch_gather_equals_two_pass_route(lib, geom, H, W, scale):
+    """SURVEY.md 8f-1 "feeding K1 directly": fsar_vit_forward_u8 evaluates resize / crop / normalise inside the patch gather
+    (uint8 THWC -> 16-bit im2col rows, no fp32 NCHW crop in HBM). It must give the frame features of the two-pass route
+    fsar_preprocess_u8 -> fsar_vit_forward, whose first half is pinned to the reference's transforms above: same fp32
+    arithmetic per pixel, same rounding to the operand type, so the patch rows -- and with them every later number -- are
+    bit-identical. Patch sizes 16 and 14 (ViT-L/14), down- and up-sampling sources."""
+    from clip_fsar_b200 import synth
+    g = dict(synth.full_geometry(geom), layers=1)
+    sd = synth.synth_state_dict(g, 5, spread=False)
+    e = lib.Engine(**dict(g, max_frames=4, max_videos=2, max_tokens=4, max_classes=4, otam_lambda=0.5, device=0))
+    e.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    frames = torch.from_numpy(synth.synth_raw_frames(6, H, W, seed=91)).cuda()          # 6 frames: two passes of <= 4
+    two_pass = e.vit_forward(e.preprocess_u8(frames, (scale, scale)))
+    fused = e.vit_forward_u8(frames, (scale, scale))
+    assert torch.isfinite(fused).all() and float(fused.abs().max()) > 0
+    assert torch.equal(fused, two_pass)
+    e.close()

@@ -42,6 +42,7 @@ for (N, K, epi, nm) in () if os.environ.get("PROBE_ONLY") == "att" else ((2304, 
     a = (torch.randn(M, K, device=DEV) * 0.1).to(dt); w = (torch.randn(N, K, device=DEV) * 0.1).to(dt); b = torch.randn(N, device=DEV)
     out = torch.zeros(M, N, device=DEV, dtype=dt if epi in (0, 1) else torch.float32)
     run("gemm_" + nm, lambda: eng.op_gemm(a, w, b, epi, out=out), 2.0 * M * N * K)
+if os.environ.get("PROBE_ONLY") == "gemm": sys.exit(0)
 qkv = torch.randn(M, 2304, device=DEV).to(dt)
 run("attention", lambda: eng.op_attention(qkv, M // 197, 197, 12), 4.0 * (M // 197) * 12 * 197 * 197 * 64)
 qkv = torch.randn(96 * 257, 3 * 1024, device=DEV).to(dt)
