@@ -78,13 +78,25 @@ class Synth_few_shot(torch.utils.data.Dataset):
             raise ValueError("TEST.CLASS_NAME lists %d classes but the episodes are %d-way: real labels would index "
                              "past text_features_test" % (self.n_cls, self.way))
         self.length = int(getattr(cfg.TRAIN, "NUM_TEST_TASKS", 100))
+        # FSAR_SYNTH_POOL=n: cycle n cached episodes (per loader worker) instead of generating every index afresh, so a
+        # throughput run through the reference runner measures the runner, not numpy's random generator
+        self.pool = int(os.environ.get("FSAR_SYNTH_POOL", "0") or 0)
+        self._cache = {}
 
     def __len__(self):
         return self.length
 
     def __getitem__(self, index):
-        ep = synth.synth_episode(self.way, self.shot, self.queries, self.frames, self.size, self.n_cls, 1000 + int(index))
-        return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in ep.items()}
+        index = int(index)
+        if self.pool > 0:
+            index %= self.pool
+            if index in self._cache:
+                return self._cache[index]
+        ep = synth.synth_episode(self.way, self.shot, self.queries, self.frames, self.size, self.n_cls, 1000 + index)
+        item = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in ep.items()}
+        if self.pool > 0:
+            self._cache[index] = item
+        return item
 
 
 def register(reference_root=None):

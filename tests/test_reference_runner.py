@@ -1,7 +1,7 @@
 """GPU: the reference's UNMODIFIED runner (runs/run.py -> runs/test_net_few_shot.py:test_few_shot / test_epoch, 35-224)
-drives the registered sm_100a head on a B200 — `NUM_GPUS: 1`, and `NUM_GPUS: 2` through the reference's own
+drives the registered sm_100a head on a B200 — `NUM_GPUS: 1`, and `NUM_GPUS: 2` / `8` through the reference's own
 `torch.multiprocessing.spawn` launcher + DistributedDataParallel wrap (utils/launcher.py:29-34, models/base/builder.py:69-79)
-when the box has two GPUs. The tree is the byte-identical copy staged by tools/stage_reference.sh under baseline/_ref
+when the box has that many GPUs. The tree is the byte-identical copy staged by tools/stage_reference.sh under baseline/_ref
 (git-ignored, travels with the gpurun snapshot); only YAML files are added next to the config they inherit from.
 
 Checked: the run finishes, the logged `val_epoch` top1_err equals what clip_fsar_b200.runner.evaluate computes in this
@@ -32,15 +32,16 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run_reference_runner(n_gpus, out_dir):
-    name = "tmp_runner_%dgpu.yaml" % n_gpus
+def _run_reference_runner(n_gpus, out_dir, n_episodes=N_EPISODES, pool=0):
+    name = "tmp_runner_%dgpu_%d.yaml" % (n_gpus, n_episodes)
     with open(os.path.join(REF, CFG_DIR, name), "w") as f:
         f.write("_BASE: ./CLIPFSAR_synth_5way1shot_vitb16_sm100.yaml\n"
                 "TRAIN:\n  NUM_TEST_TASKS: %d\n  BATCH_SIZE: %d\n"
                 "TEST:\n  BATCH_SIZE: %d\n"
-                "DATA_LOADER:\n  NUM_WORKERS: 2\n"
-                "LOG_PERIOD: 1\nNUM_GPUS: %d\nOUTPUT_DIR: %s\n" % (N_EPISODES, n_gpus, n_gpus, n_gpus, out_dir))
-    env = dict(os.environ, CLIP_FSAR_ROOT=REF, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+                "DATA_LOADER:\n  NUM_WORKERS: 4\n"
+                "LOG_PERIOD: 1\nNUM_GPUS: %d\nOUTPUT_DIR: %s\n" % (n_episodes, n_gpus, n_gpus, n_gpus, out_dir))
+    env = dict(os.environ, CLIP_FSAR_ROOT=REF, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""),
+               FSAR_SYNTH_POOL=str(pool))
     t0 = time.perf_counter()
     r = subprocess.run([sys.executable, "-m", "clip_fsar_b200.run", "--cfg", os.path.join(CFG_DIR, name),
                         "--init_method", "tcp://127.0.0.1:%d" % _free_port()],
@@ -85,7 +86,7 @@ def _expected_top1_err(n_episodes):
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "runs")), reason="reference tree not staged (tools/stage_reference.sh)")
-@pytest.mark.parametrize("n_gpus", [1, 2])
+@pytest.mark.parametrize("n_gpus", [1, 2, 8])
 def test_unmodified_reference_runner_drives_the_sm100_head(n_gpus, tmp_path):
     if torch.cuda.device_count() < n_gpus:
         pytest.skip("needs %d GPUs" % n_gpus)
@@ -94,13 +95,18 @@ def test_unmodified_reference_runner_drives_the_sm100_head(n_gpus, tmp_path):
     assert want["n_total"] == N_EPISODES * 5
     # ValMeter averages the per-iteration error rates (equal-sized episodes): the global error rate
     assert abs(float(epoch["top1_err"]) - want["top1_err"]) < 1e-3, (epoch, want)
-    # through-runner rate from the runner's own per-iteration timer (utils/meters.py:787), first iterations dropped
-    dts = [float(i["time_diff"]) for i in iters][3:]
+    # through-runner rate (SURVEY.md 8d timing protocol): a second, longer run over a pool of cached episodes so that the
+    # loader does not generate random frames per index; the runner's own per-iteration timer (utils/meters.py:787), first
+    # iterations dropped. Still inside every iteration: collation of 48 MB, .cuda(), the forward, 3 x .item() and
+    # (NUM_GPUS > 1) 3 all-reduces (test_net_few_shot.py:59-62, 168-178).
+    n_long = 160 * n_gpus
+    _, iters_long, wall_long = _run_reference_runner(n_gpus, str(tmp_path), n_episodes=n_long, pool=8)
+    dts = sorted(float(i["time_diff"]) for i in iters_long[10:])
     rec = {"n_gpus": n_gpus, "episodes": N_EPISODES, "top1_err_runner": float(epoch["top1_err"]), "top1_err_expected": want["top1_err"],
-           "wall_s_whole_run": wall,
-           "runner_episodes_per_s": (n_gpus / (sum(dts) / len(dts))) if dts else None,
-           "note": "runs/test_net_few_shot.py:test_epoch unmodified; per-iteration time includes the DataLoader, 3 x .item() and "
-                   "(NUM_GPUS > 1) 3 all-reduces per episode (test_net_few_shot.py:168-178)"}
+           "wall_s_whole_run": wall, "throughput_run_episodes": n_long, "throughput_run_wall_s": wall_long,
+           "runner_episodes_per_s_median_iter": (n_gpus / dts[len(dts) // 2]) if dts else None,
+           "runner_episodes_per_s_mean_iter": (n_gpus * len(dts) / sum(dts)) if dts else None,
+           "note": "runs/test_net_few_shot.py:test_epoch unmodified, head = CNN_OTAM_CLIPFSAR_SM100 (one episode per call)"}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "r2_reference_runner_%dgpu.json" % n_gpus), "w") as f:
         json.dump(rec, f)
