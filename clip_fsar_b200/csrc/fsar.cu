@@ -448,19 +448,20 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, T16* __restric
 // in_pitch: distance between input rows in elements (0: D); the output is always dense.
 int layernorm(fsar_handle* h, const float* x, void* out, const float* g, const float* b, int rows, int D, bool out16,
               bool embed, int tokens, const float* cls_emb, const float* pos, cudaStream_t st, int cls, int reverse = 0,
-              long long in_pitch = 0) {
+              long long in_pitch = 0, T16* out2 = nullptr, const float* g2 = nullptr, const float* b2 = nullptr) {
     if (in_pitch == 0) in_pitch = D;
     if ((D % 128) != 0 || D > 1024) return fail(h, FSAR_E_INVALID, "layernorm: dim %d must be a multiple of 128 and <= 1024", D);
     const int wpb = 8;
     const int grid = (rows + wpb - 1) / wpb;
-    Scope s(h, st, cls, 0.0, (double)rows * D * (4.0 + (out16 ? 2.0 : 4.0)));
+    Scope s(h, st, cls, 0.0, (double)rows * D * (4.0 + (out16 ? 2.0 : 4.0) + (out2 ? 2.0 : 0.0)));
     const float* np = nullptr;
+    T16* n16 = nullptr;
     if (embed)
-        launch_pdl(h, layernorm_kernel<T16, false, true>, dim3(grid), dim3(256), 0, st, x, out, g, b, rows, D, 1e-5f, tokens, cls_emb, pos, reverse, in_pitch);
+        launch_pdl(h, layernorm_kernel<T16, false, true>, dim3(grid), dim3(256), 0, st, x, out, g, b, rows, D, 1e-5f, tokens, cls_emb, pos, reverse, in_pitch, out2, g2, b2);
     else if (out16)
-        launch_pdl(h, layernorm_kernel<T16, true, false>, dim3(grid), dim3(256), 0, st, x, out, g, b, rows, D, 1e-5f, tokens, np, np, reverse, in_pitch);
+        launch_pdl(h, layernorm_kernel<T16, true, false>, dim3(grid), dim3(256), 0, st, x, out, g, b, rows, D, 1e-5f, tokens, np, np, reverse, in_pitch, n16, np, np);
     else
-        launch_pdl(h, layernorm_kernel<T16, false, false>, dim3(grid), dim3(256), 0, st, x, out, g, b, rows, D, 1e-5f, tokens, np, np, reverse, in_pitch);
+        launch_pdl(h, layernorm_kernel<T16, false, false>, dim3(grid), dim3(256), 0, st, x, out, g, b, rows, D, 1e-5f, tokens, np, np, reverse, in_pitch, n16, np, np);
     return check_launch(h, "layernorm_kernel");
 }
 
@@ -751,9 +752,10 @@ int vit_encode_gathered(fsar_handle* h, int n, float* feats_out, cudaStream_t st
     RET_IF(gemm(h, FSAR_K_GEMM_PATCH, h->patches16, h->vw.conv1, nullptr, patch32, n * G2, D,
                 h->patch_kp, EPI_STORE32, st));
     // ... and ln_pre assembles [CLS | patches] + positional embedding on the fly (few_shot.py:675-677)
+    // ... and applies ln_1 of the first block to the row while it is still in registers (x32 and ln16 in one pass)
     RET_IF(layernorm(h, patch32, h->x32, h->vw.ln_pre_g, h->vw.ln_pre_b, M, D, false,
                      true, L, h->vw.cls_emb, h->vw.pos, st,
-                     FSAR_K_LAYERNORM));
+                     FSAR_K_LAYERNORM, 0, 0, h->ln16, h->vit_blocks[0].ln1_g, h->vit_blocks[0].ln1_b));
     // Row direction alternates from kernel to kernel (dir ^= 1): every consumer walks the rows in the opposite order
     // of the producer of its big input (x32 58 MB, qkv16 87 MB, h16 116 MB at 96 frames — together more than the
     // 126 MB L2), so under LRU it starts on the rows that were written last and are still cache-resident.
@@ -761,8 +763,10 @@ int vit_encode_gathered(fsar_handle* h, int n, float* feats_out, cudaStream_t st
     const int flip = h->alternate_rows ? 1 : 0;
     for (int i = 0; i < c.layers; ++i) {
         const BlockW& bw = h->vit_blocks[i];
-        RET_IF(layernorm(h, h->x32, h->ln16, bw.ln1_g, bw.ln1_b, M, D, true, false, L,
-                         nullptr, nullptr, st, FSAR_K_LAYERNORM, dir));
+        if (i > 0) {   // block 0's ln_1 came out of the ln_pre kernel above
+            RET_IF(layernorm(h, h->x32, h->ln16, bw.ln1_g, bw.ln1_b, M, D, true, false, L,
+                             nullptr, nullptr, st, FSAR_K_LAYERNORM, dir));
+        }
         dir ^= flip;
         if (i == c.layers - 1 && h->cls_last_block && L <= CLS_ATT_MAX_L) {
             // Last block: only x[:, 0, :] survives the transformer (ln_post(x[:, 0, :]) @ proj, few_shot.py:683-686), so

@@ -159,11 +159,15 @@ __global__ void patch_gather_kernel(const float* __restrict__ frames, T16* __res
 //     t == 0 : class_embedding + positional_embedding[0]
 //     t >= 1 : patch_out[f * (tokens - 1) + t - 1] + positional_embedding[t]     (patch_out = conv1 GEMM output)
 //   so the concatenated / position-embedded sequence is never materialised before the LayerNorm.
+//   out2 != nullptr (EMBED only): the row just normalised is normalised AGAIN with (gamma2, beta2) while it is still in
+//   registers and written as 16-bit -- ln_1 of the first block applied to ln_pre's output (few_shot.py:677 then 637),
+//   which saves the first block's LayerNorm launch and its re-read of the residual stream.
 template <typename T16, bool OUT16, bool EMBED>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x, void* out, const float* __restrict__ gamma, const float* __restrict__ beta,
                  int rows, int D, float eps, int tokens, const float* __restrict__ cls_emb,
-                 const float* __restrict__ pos, int reverse, long long in_pitch) {
+                 const float* __restrict__ pos, int reverse, long long in_pitch, T16* __restrict__ out2 = nullptr,
+                 const float* __restrict__ gamma2 = nullptr, const float* __restrict__ beta2 = nullptr) {
     pdl_trigger();
     pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -226,6 +230,37 @@ layernorm_kernel(const float* x, void* out, const float* __restrict__ gamma, con
                 reinterpret_cast<uint2*>(reinterpret_cast<T16*>(out) + (size_t)row * D)[lane + 32 * i] = w;
             } else {
                 reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)row * D)[lane + 32 * i] = y;
+            }
+            if (EMBED) v[i] = y;
+        }
+    }
+    if (EMBED && out2 != nullptr) {
+        float s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < nv) s2 += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        const float mean2 = s2 / float(D);
+        float q2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < nv) {
+                const float a = v[i].x - mean2, b = v[i].y - mean2, c = v[i].z - mean2, d = v[i].w - mean2;
+                q2 += (a * a + b * b) + (c * c + d * d);
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+        const float rstd2 = 1.0f / sqrtf(q2 / float(D) + eps);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < nv) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma2) + lane + 32 * i);
+                const float4 b = __ldg(reinterpret_cast<const float4*>(beta2) + lane + 32 * i);
+                uint2 w;
+                w.x = pack2<T16>((v[i].x - mean2) * rstd2 * g.x + b.x, (v[i].y - mean2) * rstd2 * g.y + b.y);
+                w.y = pack2<T16>((v[i].z - mean2) * rstd2 * g.z + b.z, (v[i].w - mean2) * rstd2 * g.w + b.w);
+                reinterpret_cast<uint2*>(out2 + (size_t)row * D)[lane + 32 * i] = w;
             }
         }
     }
