@@ -38,6 +38,19 @@ def test_layernorm(eng, D):
     assert rel_l2(eng.op_layernorm(x, g, b, True), ref) < 4e-4                 # 16-bit output rounding only
 
 
+@pytest.mark.parametrize("rows,D", [(2048, 768), (5003, 768), (18912, 768), (4111, 1024), (3000, 512), (2500, 128)])
+def test_layernorm_full_size(eng, rows, D):
+    """Full-size launches (thousands of rows, every supported width, a row with a large dynamic range)."""
+    x = torch.randn(rows, D, device=DEV) * 3 + 1
+    x[rows // 2] *= 50.0                                                       # one row with a large dynamic range
+    g, b = torch.randn(D, device=DEV), torch.randn(D, device=DEV)
+    ref = torch.nn.functional.layer_norm(x, (D,), g, b, 1e-5)
+    out = eng.op_layernorm(x, g, b, True)
+    assert rel_l2(out, ref) < 4e-4
+    assert float((out.float() - ref).abs().max()) < 2e-2 * float(ref.abs().max())   # no row may be off
+    assert rel_l2(eng.op_layernorm(x, g, b, False), ref) < 1e-6
+
+
 def test_layernorm_rejects_unsupported_dim(eng, lib):
     x = torch.randn(4, 100, device=DEV)
     with pytest.raises(lib.FsarError):
