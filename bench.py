@@ -456,7 +456,7 @@ class Workload:
         return {"ok": bool(ok), "logits_max_rel": rel, "vit_feature_rel_l2": vit_err, "mode": mode, "bound": 1e-3}
 
 
-def gemm_roofline(prof, n_episodes, pk, clocks):
+def gemm_roofline(prof, n_episodes, pk, clocks, step_clocks=None):
     classes = [k for k in prof if k.startswith("gemm_")]
     ms = sum(prof[k]["ms"] for k in classes)
     flops = sum(prof[k]["flops"] for k in classes)
@@ -490,8 +490,15 @@ def gemm_roofline(prof, n_episodes, pk, clocks):
             "traffic": traffic, "traffic_source": "profiles/ncu_traffic.json (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum, mean over the GEMM launches)",
             "launches_per_episode": launches / n_episodes, "share_of_step": ms / total_ms if total_ms else None,
             "flops_per_episode": flops / n_episodes,
+            # the event-bracketed pass leaves gaps between kernels, draws less power and therefore clocks higher than the
+            # back-to-back sustained region: the same rate scaled to the SM clock observed THERE (tensor-bound kernel)
+            "achieved_at_step_clock": (achieved * step_clocks["sm_mhz"] / clocks["sm_mhz"]
+                                       if step_clocks and clocks and step_clocks.get("sm_mhz") and clocks.get("sm_mhz") else None),
+            "frac_at_step_clock": (achieved * step_clocks["sm_mhz"] / clocks["sm_mhz"] / pk["tf_sustained"]
+                                   if step_clocks and clocks and step_clocks.get("sm_mhz") and clocks.get("sm_mhz") else None),
             "how": "CUDA events around every launch (fsar_profile_begin/end) over %d episodes right after the sustained region; "
-                   "achieved = flops_per_launch / avg_launch_ms" % n_episodes}
+                   "achieved = flops_per_launch / avg_launch_ms; frac_at_step_clock = achieved x (SM clock of the sustained "
+                   "region / SM clock of this pass) / sustained peak" % n_episodes}
 
 
 def executed_flops(prof, n_episodes):
@@ -538,7 +545,7 @@ def run_workload(name, args, L, dev, local, dist):
     prof_calls = max(2, int(math.ceil(0.6e3 / call_ms)))
     prof, prof_clocks = W.profile(prof_calls, ClockSampler(local) if rank == 0 else None)
     NP = prof_calls * B
-    roofline = gemm_roofline(prof, NP, pk, prof_clocks)
+    roofline = gemm_roofline(prof, NP, pk, prof_clocks, clocks)
     kernels = {k: {"ms_per_episode": v["ms"] / NP, "launches_per_episode": v["launches"] / NP,
                    "tflops": (v["flops"] / v["ms"] / 1e9 if v["ms"] and v["flops"] else None),
                    "gbs": (v["bytes"] / v["ms"] / 1e6 if v["ms"] and v["bytes"] else None)} for k, v in prof.items()}

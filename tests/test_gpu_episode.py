@@ -293,6 +293,62 @@ def test_capacity_and_argument_errors(lib):
     e.close()
 
 
+def test_out_of_range_real_labels_are_reported_not_silently_wrong(lib):
+    """The reference raises IndexError at text_features_test[support_real_class.long()] (few_shot.py:2946). Here the labels
+    live on the device and no entry point synchronises: the kernels clamp the index (nothing reads out of bounds) and raise
+    a flag in mapped host memory; the host path reports it at collect (FSAR_E_INVALID), the stream-ordered path at the
+    next call on the handle. A good episode afterwards works again."""
+    meta, _ = load_golden("tiny_5w1s")
+    g, sd, tt, te, task = regenerate(meta)
+    e = make_engine(lib, meta, g, sd, tt, te)
+    good = {k: torch.from_numpy(v) for k, v in task.items()}
+    for bad_value in (float(meta["n_test"]), -1.0, float("nan"), 1.0e9):
+        bad = dict(good)
+        bad["real_support_labels"] = good["real_support_labels"].clone()
+        bad["real_support_labels"][2] = bad_value
+        args = lambda t, dev: [t[k].to(dev) if dev else t[k].pin_memory() for k in
+                               ("support_set", "target_set", "support_labels", "real_support_labels")]
+        # host path: reported by the collect of that very batch
+        with pytest.raises(lib.FsarError) as err:
+            e.episode_forward_host(*args(bad, None), meta["T"], meta["way"], n_train_classes=meta["n_train"])
+        assert err.value.code == -1 and "real_support_labels" in str(err.value)
+        # device path: the call itself is stream-ordered and returns; the NEXT call reports
+        logits, _ = e.episode_forward(*args(bad, DEV), meta["T"], meta["way"], n_train_classes=meta["n_train"])
+        torch.cuda.synchronize()
+        assert torch.isfinite(logits).all()                        # clamped, not out of bounds
+        with pytest.raises(lib.FsarError) as err:
+            e.episode_forward(*args(good, DEV), meta["T"], meta["way"], n_train_classes=meta["n_train"])
+        assert err.value.code == -1
+        ok, _ = e.episode_forward(*args(good, DEV), meta["T"], meta["way"], n_train_classes=meta["n_train"])
+        torch.cuda.synchronize()
+    ref, _ = run(e, meta, task)
+    assert torch.equal(ok, ref)
+    # fewer classes announced than the labels hold (way = 4 for a 5-class episode): flagged the same way
+    with pytest.raises(lib.FsarError) as err:
+        e.episode_forward_host(*args(good, None), meta["T"], 4, n_train_classes=meta["n_train"])
+    assert err.value.code == -1 and "way" in str(err.value)
+    e.close()
+
+
+def test_wrong_frame_geometry_is_rejected(lib):
+    """A task dict built with another DATA.TEST_CROP_SIZE must not be read with the engine's stride (silent garbage): the
+    binding raises before anything is enqueued; the reference fails with a positional_embedding shape mismatch."""
+    meta, _ = load_golden("tiny_5w1s")
+    g, sd, tt, te, task = regenerate(meta)
+    e = make_engine(lib, meta, g, sd, tt, te)
+    t = {k: torch.from_numpy(v).to(DEV) for k, v in task.items()}
+    S = g["image_size"]
+    wrong = torch.zeros(40, 3, S + 16, S + 16, device=DEV)
+    with pytest.raises(ValueError, match="image_size"):
+        e.episode_forward(wrong, t["target_set"], t["support_labels"], t["real_support_labels"], 8, 5, n_train_classes=64)
+    with pytest.raises(ValueError):
+        e.vit_forward(wrong)
+    with pytest.raises(ValueError):                                             # labels must be fp32 (ssv2_few_shot.py:278-283)
+        e.episode_forward(t["support_set"], t["target_set"], t["support_labels"].long(), t["real_support_labels"], 8, 5,
+                          n_train_classes=64)
+    e.close()
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # BASELINE.json's headline size (ViT-B/16, 5-way 1-shot, 8 x 224^2): properties that need no CPU reference
 @pytest.fixture(scope="module")
