@@ -451,6 +451,16 @@ int layernorm(fsar_handle* h, const float* x, void* out, const float* g, const f
               long long in_pitch = 0, T16* out2 = nullptr, const float* g2 = nullptr, const float* b2 = nullptr) {
     if (in_pitch == 0) in_pitch = D;
     if ((D % 128) != 0 || D > 1024) return fail(h, FSAR_E_INVALID, "layernorm: dim %d must be a multiple of 128 and <= 1024", D);
+    if (out16 && !embed && in_pitch == D && (D == 512 || D == 768 || D == 1024)) {
+        // dense rows -> 16-bit, the CLIP widths: the instance with the width compiled in (vit_kernels.cuh)
+        Scope s(h, st, cls, 0.0, (double)rows * D * 6.0);
+        T16* o16 = reinterpret_cast<T16*>(out);
+        const int grid16 = (rows + 7) / 8;
+        if (D == 768) launch_pdl(h, layernorm16_kernel<T16, 6>, dim3(grid16), dim3(256), 0, st, x, o16, g, b, rows, 1e-5f, reverse);
+        else if (D == 1024) launch_pdl(h, layernorm16_kernel<T16, 8>, dim3(grid16), dim3(256), 0, st, x, o16, g, b, rows, 1e-5f, reverse);
+        else launch_pdl(h, layernorm16_kernel<T16, 4>, dim3(grid16), dim3(256), 0, st, x, o16, g, b, rows, 1e-5f, reverse);
+        return check_launch(h, "layernorm16_kernel");
+    }
     const int wpb = 8;
     const int grid = (rows + wpb - 1) / wpb;
     Scope s(h, st, cls, 0.0, (double)rows * D * (4.0 + (out16 ? 2.0 : 4.0) + (out2 ? 2.0 : 0.0)));
