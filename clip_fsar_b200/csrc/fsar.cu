@@ -61,7 +61,7 @@ struct Weight {
 // heads of the episodes of one fsar_episodes_* call can run concurrently on side streams.
 struct HeadWs {
     float *seq = nullptr, *mod_ln = nullptr, *mod_qkvbuf = nullptr, *mod_att = nullptr, *mod_y = nullptr, *mod_h = nullptr,
-          *mod_out = nullptr, *mod_tmp = nullptr;
+          *mod_out = nullptr, *mod_tmp = nullptr, *mod_part = nullptr;
     float *protos = nullptr, *dists = nullptr, *cum = nullptr;
     int *cls = nullptr, *counts = nullptr;
 };
@@ -162,6 +162,9 @@ struct fsar_handle {
     bool cls_last_block = true;     // FSAR_FULL_LAST_BLOCK=1: the last block also computes the token rows nobody reads
                                     // (tests/test_gpu_episode.py proves both give the same frame features)
     bool pdl = true;                // FSAR_NO_PDL=1: no programmatic dependent launch between the frame-encoder kernels
+    bool mod_fused = true;          // single-episode calls run a modulator layer as ONE cooperative kernel (probes build:
+                                    // FSAR_NO_MOD_FUSED=1 keeps the six launches for A/B)
+    int mod_fused_ctas_per_sm = 0;  // co-resident CTAs per SM of modulator_fused_kernel (0: cooperative launch unavailable)
     // A/B switches that only exist in the -DFSAR_PROBES build (libfsar_sm100_probes.so, tools/gemm_probe.py); in the
     // product library they are compile-time constants and the alternative code paths are not compiled in:
     bool alternate_rows = true;     // FSAR_NO_ALTERNATE=1: every kernel walks rows first-to-last
@@ -707,6 +710,7 @@ int alloc_workspace(fsar_handle* h) {
         RET_IF(dalloc(h, &w.mod_h, rows * (size_t)c.mod_mlp_dim));
         RET_IF(dalloc(h, &w.mod_out, rows * E));
         RET_IF(dalloc(h, &w.mod_tmp, rows * E));
+        RET_IF(dalloc(h, &w.mod_part, MODF_KSPLIT * rows * E));
         RET_IF(dalloc(h, &w.protos, V * T * E));
         RET_IF(dalloc(h, &w.dists, V * V * T * T));
         RET_IF(dalloc(h, &w.cum, V * V));
@@ -886,16 +890,47 @@ int vit_encode_segments(fsar_handle* h, const float* const* ptrs, const int* cou
 
 // ---------------------------------------------------------------- temporal prototype modulator
 // x [rows, E]: n_q sequences of T tokens followed by n_s sequences of T + 1 tokens -> out [rows, E]
-int modulate_rows(fsar_handle* h, HeadWs& w, const float* x, int n_q, int n_s, int T, float* out, cudaStream_t st) {
+size_t mod_fused_smem(const fsar_config& c, int T) {
+    const size_t nmax = (size_t)T + 1;
+    const size_t att = sizeof(float) * (3 * nmax * c.mod_dim_head + nmax * (nmax + 1));
+    return att > sizeof(LinSmem) ? att : sizeof(LinSmem);
+}
+
+// `fused`: one cooperative launch per layer (modulator_fused_kernel) instead of six. Used when the call holds ONE episode
+// (the nn.Module path, fsar_modulate): with several episodes per call their heads run concurrently on side streams, where
+// six small launches per head overlap better than cooperative grids that each want every SM.
+int modulate_rows(fsar_handle* h, HeadWs& w, const float* x, int n_q, int n_s, int T, float* out, cudaStream_t st,
+                  bool fused = false) {
     const fsar_config& c = h->cfg;
     const int E = c.embed_dim, inner = c.mod_heads * c.mod_dim_head, F = c.mod_mlp_dim;
     const int rows = n_q * T + n_s * (T + 1);
     if (T + 1 > MOD_MAX_TOK) return fail(h, FSAR_E_INVALID, "modulator: %d tokens per sequence exceeds %d", T + 1, MOD_MAX_TOK);
     const float* cur = x;
+    fused = fused && h->mod_fused && h->mod_fused_ctas_per_sm > 0 && (F % (MODF_KSPLIT * LIN_BK * LIN_WARPS)) == 0 &&
+            (E % (LIN_BK * LIN_WARPS)) == 0 && (inner % (LIN_BK * LIN_WARPS)) == 0;
     for (int l = 0; l < c.mod_depth; ++l) {
         const ModW& mw = h->mod_layers[l];
         // depth > 1: intermediate layers ping-pong between mod_tmp and seq (seq is dead once layer 0 consumed it)
         float* dst = (l == c.mod_depth - 1) ? out : ((l & 1) ? w.seq : w.mod_tmp);
+        if (fused) {
+            ModFusedParams mp{};
+            mp.x = cur; mp.out = dst;
+            mp.n_q = n_q; mp.n_s = n_s; mp.T = T; mp.E = E; mp.inner = inner; mp.F = F; mp.heads = c.mod_heads; mp.dh = c.mod_dim_head;
+            mp.scale = 1.0f / sqrtf((float)c.mod_dim_head); mp.eps = 1e-5f;
+            mp.norm_g = mw.norm_g; mp.norm_b = mw.norm_b; mp.w_qkv = mw.qkv; mp.w_out = mw.w_out; mp.b_out = mw.b_out;
+            mp.w_fc = mw.w_fc; mp.b_fc = mw.b_fc; mp.w_proj = mw.w_proj; mp.b_proj = mw.b_proj;
+            mp.ln = w.mod_ln; mp.qkv = w.mod_qkvbuf; mp.att = w.mod_att; mp.y = w.mod_y; mp.hid = w.mod_h; mp.part = w.mod_part;
+            const size_t smem = mod_fused_smem(c, T);
+            const int per_sm = h->mod_fused_ctas_per_sm < 3 ? h->mod_fused_ctas_per_sm : 3;   // measured: 1 -> 105, 2 -> 101, 3 -> 92, 4 -> 114 us
+            Scope s(h, st, FSAR_K_MODULATOR, 2.0 * rows * ((double)3 * inner * E + (double)E * inner + 2.0 * E * F) + 4.0 * rows * (T + 1) * inner,
+                    4.0 * ((double)3 * inner * E + (double)E * inner + 2.0 * E * F));
+            void* args[] = {&mp};
+            cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(modulator_fused_kernel), dim3(per_sm * h->sms),
+                                                        dim3(LIN_THREADS), args, smem, st);
+            if (e != cudaSuccess) return fail(h, FSAR_E_CUDA, "cooperative launch of modulator_fused_kernel failed: %s", cudaGetErrorString(e));
+            cur = dst;
+            continue;
+        }
         RET_IF(layernorm(h, cur, w.mod_ln, mw.norm_g, mw.norm_b, rows, E, false, false,
                          1, nullptr, nullptr, st, FSAR_K_MODULATOR));
         RET_IF(linear_f32<LIN_NONE>(h, w.mod_ln, mw.qkv, nullptr, nullptr, w.mod_qkvbuf, rows, 3 * inner, E, st));
@@ -933,7 +968,7 @@ int otam_logits(fsar_handle* h, const float* q, const float* protos, int Q, int 
 // class_logits.
 int head_forward(fsar_handle* h, HeadWs& w, const float* sup, const float* tgt, const float* support_labels,
                  const float* real_support_labels, int S, int Q, int T, int way, int merge_before, int single_direct,
-                 int text_mode, float text_coff, float* logits, float* class_logits, cudaStream_t st) {
+                 int text_mode, float text_coff, float* logits, float* class_logits, cudaStream_t st, bool fused_modulator) {
     const fsar_config& c = h->cfg;
     const int E = c.embed_dim;
     if (text_mode < 0 || text_mode > 2) return fail(h, FSAR_E_INVALID, "episode: text_mode %d not in {0, 1, 2}", text_mode);
@@ -974,7 +1009,7 @@ int head_forward(fsar_handle* h, HeadWs& w, const float* sup, const float* tgt, 
     }
     // depth > 1 uses w.seq as a ping-pong buffer, so the first layer must not read it after layer 2 wrote it:
     // layer l reads `cur` and writes dst != cur, and w.seq is only overwritten at l = 1 (after l = 0 consumed it).
-    RET_IF(modulate_rows(h, w, w.seq, Q, n_sup_seq, T, w.mod_out, st));
+    RET_IF(modulate_rows(h, w, w.seq, Q, n_sup_seq, T, w.mod_out, st, fused_modulator));
     {
         Scope s(h, st, FSAR_K_HEAD_MISC, 0.0, 8.0 * way * T * E);
         launch_pdl(h, prototype_kernel, dim3(way * T), dim3(128), 0, st, w.mod_out, Q * T, n_sup_seq, T, E, w.cls, w.counts, merge_before,
@@ -1043,7 +1078,7 @@ int episodes_forward_dev(fsar_handle* h, const fsar_episode* eps, int n, float* 
                                      sizeof(float) * (size_t)(ep.n_support + ep.n_target) * h->n_text_train, hs));
         RET_IF(head_forward(h, h->ws[i], sup, tgt, ep.support_labels, ep.real_support_labels, ep.n_support, ep.n_target, T,
                             ep.way, ep.merge_before, ep.single_direct, ep.text_mode, ep.text_coff, logits + l_off,
-                            class_logits ? class_logits + c_off : nullptr, hs));
+                            class_logits ? class_logits + c_off : nullptr, hs, /*fused_modulator=*/n == 1));
         if (fork) {
             CU_OK(h, cudaEventRecord(h->head_done[i], hs));
             CU_OK(h, cudaStreamWaitEvent(st, h->head_done[i], 0));
@@ -1130,6 +1165,8 @@ int fsar_create(const fsar_config* cfg, fsar_handle** out) {
         e = getenv("FSAR_NO_PDL");
         h->pdl = !(e != nullptr && e[0] == '1');
 #ifdef FSAR_PROBES
+        e = getenv("FSAR_NO_MOD_FUSED");
+        h->mod_fused = !(e != nullptr && e[0] == '1');
         e = getenv("FSAR_LEGACY_ATTENTION");
         h->legacy_attention = (e != nullptr && e[0] == '1');
         e = getenv("FSAR_NO_ALTERNATE");
@@ -1173,6 +1210,17 @@ int fsar_create(const fsar_config* cfg, fsar_handle** out) {
         }
         if ((rc = alloc_weights(h)) != 0) break;
         if ((rc = alloc_workspace(h)) != 0) break;
+        {   // the fused modulator layer needs a cooperative launch: how many of its CTAs are co-resident per SM?
+            int coop = 0, per_sm = 0;
+            const size_t smem = mod_fused_smem(c, c.max_tokens);
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.device);
+            if (coop && (smem <= 48 * 1024 || cudaFuncSetAttribute(modulator_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                                   (int)smem) == cudaSuccess) &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, modulator_fused_kernel, LIN_THREADS, smem) == cudaSuccess)
+                h->mod_fused_ctas_per_sm = per_sm;
+            else
+                cudaGetLastError();
+        }
         if (cudaHostAlloc(reinterpret_cast<void**>(&h->status_host), 64, cudaHostAllocMapped) != cudaSuccess ||
             cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->status_dev), h->status_host, 0) != cudaSuccess) {
             rc = fail(nullptr, FSAR_E_NOMEM, "cannot allocate the mapped status word");
@@ -1204,8 +1252,8 @@ void fsar_destroy(fsar_handle* h) {
                     h->cls_q16, h->cls_att16, h->cls_ln16, h->cls_h16};
     for (void* p : bufs) if (p) cudaFree(p);
     for (HeadWs& w : h->ws) {
-        void* wb[] = {w.seq, w.mod_ln, w.mod_qkvbuf, w.mod_att, w.mod_y, w.mod_h, w.mod_out, w.mod_tmp, w.protos, w.dists, w.cum,
-                      w.cls, w.counts};
+        void* wb[] = {w.seq, w.mod_ln, w.mod_qkvbuf, w.mod_att, w.mod_y, w.mod_h, w.mod_out, w.mod_tmp, w.mod_part, w.protos, w.dists,
+                      w.cum, w.cls, w.counts};
         for (void* p : wb) if (p) cudaFree(p);
     }
     for (cudaStream_t st : h->head_streams) if (st) cudaStreamDestroy(st);
@@ -1292,7 +1340,7 @@ int fsar_modulate(fsar_handle* h, const float* x_dev, int n_seq, int n_tok, floa
     if ((size_t)n_seq * n_tok > (size_t)h->cfg.max_videos * (h->cfg.max_tokens + 1))
         return fail(h, FSAR_E_STATE, "fsar_modulate: %d x %d rows exceed the workspace", n_seq, n_tok);
     // all sequences have n_tok tokens: express as n_seq "query" sequences of T = n_tok
-    return modulate_rows(h, h->ws[0], x_dev, n_seq, 0, n_tok, out_dev, (cudaStream_t)stream);
+    return modulate_rows(h, h->ws[0], x_dev, n_seq, 0, n_tok, out_dev, (cudaStream_t)stream, /*fused=*/true);
 }
 
 int fsar_otam_logits(fsar_handle* h, const float* q_dev, const float* protos_dev, int Q, int way, int T, int single_direct,

@@ -5,6 +5,7 @@
 //   Attention_qkv 1035-1073, FeedForward 1643-1654, OTAM_cum_dist_v2 2657-2687,
 //   CNN_OTAM_CLIPFSAR.forward eval branch 2932-2990.
 #pragma once
+#include <cooperative_groups.h>
 #include "ptx.cuh"
 
 namespace fsar {
@@ -157,20 +158,22 @@ build_sequences_kernel(const float* __restrict__ sup, const float* __restrict__ 
 enum LinAct : int { LIN_NONE = 0, LIN_GELU = 1 };
 constexpr int LIN_BM = 16, LIN_BN = 32, LIN_BK = 32, LIN_WARPS = 4, LIN_THREADS = 32 * LIN_WARPS;
 
-template <int ACT>
-__global__ void __launch_bounds__(LIN_THREADS)
-linear_f32_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
-                  const float* residual, float* C, int R, int N, int K) {
-    pdl_trigger();   // programmatic dependent launch: see ptx.cuh
-    pdl_wait();
-    __shared__ __align__(16) float sA[LIN_WARPS][LIN_BK][LIN_BM + 4];   // [warp][k][row]
-    __shared__ __align__(16) float sW[LIN_WARPS][LIN_BK][LIN_BN + 4];   // [warp][k][col]
-    const int r0 = blockIdx.y * LIN_BM, n0 = blockIdx.x * LIN_BN;
+// One 16 x 32 output tile at (r0, n0) over the K range [kofs, kofs + klen) (klen % 128 == 0), by one CTA of 128 threads.
+// `partial` != nullptr: write the raw partial sums there (split-K over CTAs; bias / activation / residual are applied by
+// whoever combines the partials); else finish the tile: + bias, activation, + residual -> C.
+struct LinSmem {
+    float a[LIN_WARPS][LIN_BK][LIN_BM + 4];   // [warp][k][row]
+    float w[LIN_WARPS][LIN_BK][LIN_BN + 4];   // [warp][k][col]
+};
+template <int ACT, bool PREFETCH_ALL>
+__device__ __forceinline__ void linear_f32_tile(LinSmem& sm, const float* __restrict__ A, const float* __restrict__ W,
+                                                const float* __restrict__ bias, const float* residual, float* C,
+                                                float* partial, int R, int N, int K, int r0, int n0, int kofs, int klen) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ty = lane >> 3;  // rows ty * 4 .. + 3
     const int tx = lane & 7;   // cols tx * 4 .. + 3
-    const int kspan = K / LIN_WARPS;
-    const int kbeg = warp * kspan, kend = kbeg + kspan;
+    const int kspan = klen / LIN_WARPS;
+    const int kbeg = kofs + warp * kspan, kend = kbeg + kspan;
     // loader mapping: one float4 along K per (row, lane & 7); 4 rows of 8 float4 per pass
     const int lrow = lane >> 3, lk = (lane & 7) * 4;
     float4 ra[4], rw[8];
@@ -187,22 +190,21 @@ linear_f32_kernel(const float* __restrict__ A, const float* __restrict__ W, cons
         }
     };
     float acc[4][4] = {};
-    float (*a_s)[LIN_BM + 4] = sA[warp];
-    float (*w_s)[LIN_BN + 4] = sW[warp];
-    fetch(kbeg);
-    for (int k0 = kbeg; k0 < kend; k0 += LIN_BK) {
+    float (*a_s)[LIN_BM + 4] = sm.a[warp];
+    float (*w_s)[LIN_BN + 4] = sm.w[warp];
+    auto stage = [&](const float4 (&pa)[4], const float4 (&pw)[8]) {   // registers -> this warp's k-major slabs
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int r = lrow + 4 * i;
-            a_s[lk][r] = ra[i].x; a_s[lk + 1][r] = ra[i].y; a_s[lk + 2][r] = ra[i].z; a_s[lk + 3][r] = ra[i].w;
+            a_s[lk][r] = pa[i].x; a_s[lk + 1][r] = pa[i].y; a_s[lk + 2][r] = pa[i].z; a_s[lk + 3][r] = pa[i].w;
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int n = lrow + 4 * i;
-            w_s[lk][n] = rw[i].x; w_s[lk + 1][n] = rw[i].y; w_s[lk + 2][n] = rw[i].z; w_s[lk + 3][n] = rw[i].w;
+            w_s[lk][n] = pw[i].x; w_s[lk + 1][n] = pw[i].y; w_s[lk + 2][n] = pw[i].z; w_s[lk + 3][n] = pw[i].w;
         }
-        __syncwarp();
-        if (k0 + LIN_BK < kend) fetch(k0 + LIN_BK);   // in flight while this slab is multiplied
+    };
+    auto multiply = [&]() {
 #pragma unroll
         for (int k = 0; k < LIN_BK; ++k) {
             const float4 a = *reinterpret_cast<const float4*>(&a_s[k][ty * 4]);
@@ -216,11 +218,48 @@ linear_f32_kernel(const float* __restrict__ A, const float* __restrict__ W, cons
             acc[3][0] = fmaf(a.w, w.x, acc[3][0]); acc[3][1] = fmaf(a.w, w.y, acc[3][1]);
             acc[3][2] = fmaf(a.w, w.z, acc[3][2]); acc[3][3] = fmaf(a.w, w.w, acc[3][3]);
         }
-        __syncwarp();
+    };
+    if (PREFETCH_ALL && kspan == 4 * LIN_BK) {
+        // K range of 512 (every modulator linear at embed_dim 512: K = 512, or c_proj split four ways): ALL four slabs of
+        // this warp are requested before the first FMA -- 48 float4 per lane in flight -- because the weights come cold
+        // from HBM and a one-slab-ahead pipeline pays the latency four times (same order of FMAs: same numbers). Measured:
+        // the six-launch modulator 0.1155 -> 0.0966 ms per episode. The fused cooperative kernel keeps the one-slab
+        // pipeline (PREFETCH_ALL = false): with 224 registers only two of its CTAs fit per SM and it ran 0.132 vs 0.093 ms
+        float4 pa[4][4], pw[4][8];
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+            const int k0 = kbeg + sl * LIN_BK;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = r0 + lrow + 4 * i;
+                pa[sl][i] = (r < R) ? *reinterpret_cast<const float4*>(A + (size_t)r * K + k0 + lk) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int n = n0 + lrow + 4 * i;
+                pw[sl][i] = (n < N) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)n * K + k0 + lk)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+            stage(pa[sl], pw[sl]);
+            __syncwarp();
+            multiply();
+            __syncwarp();
+        }
+    } else {
+        fetch(kbeg);
+        for (int k0 = kbeg; k0 < kend; k0 += LIN_BK) {
+            stage(ra, rw);
+            __syncwarp();
+            if (k0 + LIN_BK < kend) fetch(k0 + LIN_BK);   // in flight while this slab is multiplied
+            multiply();
+            __syncwarp();
+        }
     }
     // combine the four K-partials in a fixed order: red[warp][row][col] aliases the (now dead) weight slabs
     __syncthreads();
-    float* red = &sW[0][0][0];   // 4 * 16 * 32 floats = 8 KB <= sizeof(sW)
+    float* red = &sm.w[0][0][0];   // 4 * 16 * 32 floats = 8 KB <= sizeof(sm.w)
 #pragma unroll
     for (int i = 0; i < 4; ++i)
         *reinterpret_cast<float4*>(red + ((warp * LIN_BM + ty * 4 + i) * LIN_BN + tx * 4)) =
@@ -234,6 +273,7 @@ linear_f32_kernel(const float* __restrict__ A, const float* __restrict__ W, cons
         const float4 t = *reinterpret_cast<const float4*>(red + ((wv * LIN_BM + orow) * LIN_BN + ocol));
         v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
     }
+    __syncthreads();               // the slabs are reused by the caller's next tile
     const int r = r0 + orow;
     if (r >= R) return;
     float o[4] = {v.x, v.y, v.z, v.w};
@@ -242,11 +282,25 @@ linear_f32_kernel(const float* __restrict__ A, const float* __restrict__ W, cons
         const int n = n0 + ocol + j;
         if (n >= N) continue;
         float y = o[j];
+        if (partial != nullptr) {
+            partial[(size_t)r * N + n] = y;
+            continue;
+        }
         if (bias != nullptr) y += bias[n];
         if (ACT == LIN_GELU) y = 0.5f * y * (1.0f + erff(y * 0.70710678118654752440f));  // nn.GELU() exact
         if (residual != nullptr) y += residual[(size_t)r * N + n];
         C[(size_t)r * N + n] = y;
     }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(LIN_THREADS)
+linear_f32_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
+                  const float* residual, float* C, int R, int N, int K) {
+    pdl_trigger();   // programmatic dependent launch: see ptx.cuh
+    pdl_wait();
+    __shared__ __align__(16) LinSmem sm;
+    linear_f32_tile<ACT, true>(sm, A, W, bias, residual, C, nullptr, R, N, K, blockIdx.y * LIN_BM, blockIdx.x * LIN_BN, 0, K);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -296,6 +350,172 @@ modulator_attention_kernel(const float* __restrict__ q, const float* __restrict_
         float acc = 0.f;
         for (int b = 0; b < n; ++b) acc = fmaf(sp[a * (n + 1) + b], sv[b * dh + d], acc);
         o[(size_t)(row0 + a) * inner + head * dh + d] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One Transformer_v1 layer as ONE persistent cooperative kernel (few_shot.py:990-999):
+//   LN -> fused QKV projection -> 8-head attention in shared memory -> out-proj + bias + residual -> FFN (Linear + exact
+//   GELU, Linear split-K over CTAs) + bias + residual,
+// seven phases separated by grid barriers instead of six launches. Every phase is spread over the whole grid (the modulator
+// is 0.54 GFLOP of fp32 FMAs over 12.6 MB of weights: it needs all SMs, not one cluster); the linears run the tile routine
+// of linear_f32_kernel (same numbers), the last one split four ways along K so that 384 CTAs stream c_proj instead of 96
+// walking 16 dependent slabs each; the partials are combined in a fixed order (deterministic).
+// Launched with cudaLaunchCooperativeKernel (co-residency of the grid is guaranteed by the launch, no hand-made barrier).
+struct ModFusedParams {
+    const float* x;      // [rows, E]: n_q sequences of T tokens, then n_s sequences of T + 1 tokens
+    float* out;          // [rows, E]
+    int n_q, n_s, T, E, inner, F, heads, dh;
+    float scale, eps;
+    const float *norm_g, *norm_b, *w_qkv, *w_out, *b_out, *w_fc, *b_fc, *w_proj, *b_proj;
+    float *ln, *qkv, *att, *y, *hid, *part;   // scratch: [rows,E] [rows,3 inner] [rows,inner] [rows,E] [rows,F] [4][rows,E]
+};
+constexpr int MODF_KSPLIT = 4;
+
+__global__ void __launch_bounds__(LIN_THREADS)
+modulator_fused_kernel(const ModFusedParams p) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) uint8_t modf_smem[];     // LinSmem (linear phases) | q, k, v, p tiles (attention phase)
+    LinSmem& sm = *reinterpret_cast<LinSmem*>(modf_smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rows = p.n_q * p.T + p.n_s * (p.T + 1);
+    const int mt = (rows + LIN_BM - 1) / LIN_BM;
+    const int E = p.E;
+
+    // ---- phase 1: the shared LayerNorm of q / k / v (PreNormattention_qkv, few_shot.py:974-977), one warp per row
+    {
+        const int nv = E >> 7;
+        for (int row = blockIdx.x * LIN_WARPS + warp; row < rows; row += gridDim.x * LIN_WARPS) {
+            float4 v[8];
+            const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)row * E);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < nv) v[i] = xr[lane + 32 * i];
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < nv) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            s = warp_sum(s);
+            const float mean = s / float(E);
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < nv) {
+                    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+                    q += (a * a + b * b) + (c * c + d * d);
+                }
+            q = warp_sum(q);
+            const float rstd = 1.0f / sqrtf(q / float(E) + p.eps);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < nv) {
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(p.norm_g) + lane + 32 * i);
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.norm_b) + lane + 32 * i);
+                    float4 y;
+                    y.x = (v[i].x - mean) * rstd * g.x + b.x;
+                    y.y = (v[i].y - mean) * rstd * g.y + b.y;
+                    y.z = (v[i].z - mean) * rstd * g.z + b.z;
+                    y.w = (v[i].w - mean) * rstd * g.w + b.w;
+                    reinterpret_cast<float4*>(p.ln + (size_t)row * E)[lane + 32 * i] = y;
+                }
+        }
+    }
+    grid.sync();
+    // ---- phase 2: to_q | to_k | to_v in one [3 inner, E] projection, no bias (few_shot.py:1046-1048)
+    {
+        const int N = 3 * p.inner, nt = (N + LIN_BN - 1) / LIN_BN;
+        for (int t = blockIdx.x; t < mt * nt; t += gridDim.x)
+            linear_f32_tile<LIN_NONE, false>(sm, p.ln, p.w_qkv, nullptr, nullptr, p.qkv, nullptr, rows, N, E, (t / nt) * LIN_BM,
+                                      (t % nt) * LIN_BN, 0, E);
+    }
+    grid.sync();
+    // ---- phase 3: softmax(q k^T dh^-1/2) v per (sequence, head) in shared memory (Attention_qkv.forward, 1055-1073)
+    {
+        float* fsm = reinterpret_cast<float*>(modf_smem);
+        const int n_seq = p.n_q + p.n_s, pitch = 3 * p.inner, dh = p.dh;
+        for (int it = blockIdx.x; it < n_seq * p.heads; it += gridDim.x) {
+            const int seq = it / p.heads, head = it - seq * p.heads;
+            int row0, n;
+            if (seq < p.n_q) { row0 = seq * p.T; n = p.T; }
+            else { row0 = p.n_q * p.T + (seq - p.n_q) * (p.T + 1); n = p.T + 1; }
+            float* sq = fsm;
+            float* sk = sq + n * dh;
+            float* sv = sk + n * dh;
+            float* sp = sv + n * dh;
+            for (int i = threadIdx.x; i < n * dh; i += blockDim.x) {
+                const int t = i / dh, d = i - t * dh;
+                const size_t g = (size_t)(row0 + t) * pitch + head * dh + d;
+                sq[i] = p.qkv[g]; sk[i] = p.qkv[g + p.inner]; sv[i] = p.qkv[g + 2 * p.inner];
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
+                const int a = i / n, b = i - a * n;
+                float dot = 0.f;
+                for (int d = 0; d < dh; ++d) dot = fmaf(sq[a * dh + d], sk[b * dh + d], dot);
+                sp[a * (n + 1) + b] = dot * p.scale;
+            }
+            __syncthreads();
+            for (int a = threadIdx.x; a < n; a += blockDim.x) {
+                float mx = -INFINITY;
+                for (int b = 0; b < n; ++b) mx = fmaxf(mx, sp[a * (n + 1) + b]);
+                float sum = 0.f;
+                for (int b = 0; b < n; ++b) { const float e = expf(sp[a * (n + 1) + b] - mx); sp[a * (n + 1) + b] = e; sum += e; }
+                const float inv = 1.0f / sum;
+                for (int b = 0; b < n; ++b) sp[a * (n + 1) + b] *= inv;
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < n * dh; i += blockDim.x) {
+                const int a = i / dh, d = i - a * dh;
+                float acc = 0.f;
+                for (int b = 0; b < n; ++b) acc = fmaf(sp[a * (n + 1) + b], sv[b * dh + d], acc);
+                p.att[(size_t)(row0 + a) * p.inner + head * dh + d] = acc;
+            }
+            __syncthreads();   // the tiles are refilled by the next item
+        }
+    }
+    grid.sync();
+    // ---- phase 4: to_out + bias + residual (few_shot.py:1050-1053, 992): y = att W_o^T + b_o + x
+    {
+        const int nt = (E + LIN_BN - 1) / LIN_BN;
+        for (int t = blockIdx.x; t < mt * nt; t += gridDim.x)
+            linear_f32_tile<LIN_NONE, false>(sm, p.att, p.w_out, p.b_out, p.x, p.y, nullptr, rows, E, p.inner, (t / nt) * LIN_BM,
+                                      (t % nt) * LIN_BN, 0, p.inner);
+    }
+    grid.sync();
+    // ---- phase 5: FeedForward.net.0 + exact GELU (few_shot.py:1646-1648)
+    {
+        const int nt = (p.F + LIN_BN - 1) / LIN_BN;
+        for (int t = blockIdx.x; t < mt * nt; t += gridDim.x)
+            linear_f32_tile<LIN_GELU, false>(sm, p.y, p.w_fc, p.b_fc, nullptr, p.hid, nullptr, rows, p.F, E, (t / nt) * LIN_BM,
+                                      (t % nt) * LIN_BN, 0, E);
+    }
+    grid.sync();
+    // ---- phase 6: FeedForward.net.3, split four ways along K: partial sums
+    {
+        const int nt = (E + LIN_BN - 1) / LIN_BN, klen = p.F / MODF_KSPLIT;
+        for (int it = blockIdx.x; it < mt * nt * MODF_KSPLIT; it += gridDim.x) {
+            const int ks = it % MODF_KSPLIT, t = it / MODF_KSPLIT;
+            linear_f32_tile<LIN_NONE, false>(sm, p.hid, p.w_proj, nullptr, nullptr, nullptr, p.part + (size_t)ks * rows * E, rows, E, p.F,
+                                      (t / nt) * LIN_BM, (t % nt) * LIN_BN, ks * klen, klen);
+        }
+    }
+    grid.sync();
+    // ---- phase 7: out = ((p0 + p1) + (p2 + p3)) + b_proj + y   (few_shot.py:1654, 993)
+    {
+        const size_t n4 = (size_t)rows * E / 4, stride = (size_t)rows * E / 4;
+        const float4* part = reinterpret_cast<const float4*>(p.part);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+            const float4 a = part[i], b = part[i + stride], c = part[i + 2 * stride], d = part[i + 3 * stride];
+            const float4 bias = __ldg(reinterpret_cast<const float4*>(p.b_proj) + (i % (size_t)(E / 4)));
+            const float4 r = reinterpret_cast<const float4*>(p.y)[i];
+            float4 o;
+            o.x = ((a.x + b.x) + (c.x + d.x)) + bias.x + r.x;
+            o.y = ((a.y + b.y) + (c.y + d.y)) + bias.y + r.y;
+            o.z = ((a.z + b.z) + (c.z + d.z)) + bias.z + r.z;
+            o.w = ((a.w + b.w) + (c.w + d.w)) + bias.w + r.w;
+            reinterpret_cast<float4*>(p.out)[i] = o;
+        }
     }
 }
 
