@@ -1,13 +1,13 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-nvidia-smi topo -m 2>/dev/null | head -14 > gpurun_out/r2_topo_8gpu.txt
-lscpu | grep -i "numa\|socket\|model name\|^CPU(s)" >> gpurun_out/r2_topo_8gpu.txt
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
-( time timeout 600 $TR --master-port 29531 bench.py --gpus 8 --no-cpu-baseline ) > gpurun_out/r2_final_bench_8gpu.json 2> gpurun_out/r2_final_bench_8gpu.err
-tail -3 gpurun_out/r2_final_bench_8gpu.err
-python -c "
+( timeout 300 python -m pytest tests/test_gpu_episode.py tests/test_preprocess.py -m gpu -q -x ) > gpurun_out/r2_c20_pytest.log 2>&1
+tail -3 gpurun_out/r2_c20_pytest.log
+for d in 1 0 1 0 1 0; do
+  if [ $d = 1 ]; then export FSAR_NO_PRE=1; else unset FSAR_NO_PRE; fi
+  timeout 300 python bench.py --no-extras --no-cpu-baseline --no-parity > gpurun_out/r2_c20_bench_nopre$d.json 2> gpurun_out/r2_c20.err
+  python -c "
 import json
-d=json.load(open('gpurun_out/r2_final_bench_8gpu.json'))
-print({k:d[k] for k in ('value','n_gpus','steps','counters','numa')}); print('e2e', d['e2e']['value'], 'e2e_u8', d['e2e_u8']['value'], 'module', d['module_path']['value'])
+d=json.load(open('gpurun_out/r2_c20_bench_nopre$d.json'))
+print('nopre=$d value %.1f clk %s' % (d['value'], d['clocks']['sm_mhz']))
 "
-cat gpurun_out/r2_topo_8gpu.txt | tail -8
+done
