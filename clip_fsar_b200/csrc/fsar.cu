@@ -165,6 +165,7 @@ struct fsar_handle {
     bool mod_fused = true;          // single-episode calls run a modulator layer as ONE cooperative kernel (probes build:
                                     // FSAR_NO_MOD_FUSED=1 keeps the six launches for A/B)
     int mod_fused_ctas_per_sm = 0;  // co-resident CTAs per SM of modulator_fused_kernel (0: cooperative launch unavailable)
+    size_t mod_fused_smem_max = 0;  // dynamic shared memory the kernel was sized (and opted in) for at fsar_create
     // A/B switches that only exist in the -DFSAR_PROBES build (libfsar_sm100_probes.so, tools/gemm_probe.py); in the
     // product library they are compile-time constants and the alternative code paths are not compiled in:
     bool alternate_rows = true;     // FSAR_NO_ALTERNATE=1: every kernel walks rows first-to-last
@@ -906,7 +907,8 @@ int modulate_rows(fsar_handle* h, HeadWs& w, const float* x, int n_q, int n_s, i
     const int rows = n_q * T + n_s * (T + 1);
     if (T + 1 > MOD_MAX_TOK) return fail(h, FSAR_E_INVALID, "modulator: %d tokens per sequence exceeds %d", T + 1, MOD_MAX_TOK);
     const float* cur = x;
-    fused = fused && h->mod_fused && h->mod_fused_ctas_per_sm > 0 && (F % (MODF_KSPLIT * LIN_BK * LIN_WARPS)) == 0 &&
+    fused = fused && h->mod_fused && h->mod_fused_ctas_per_sm > 0 && mod_fused_smem(c, T) <= h->mod_fused_smem_max &&
+            (F % (MODF_KSPLIT * LIN_BK * LIN_WARPS)) == 0 &&
             (E % (LIN_BK * LIN_WARPS)) == 0 && (inner % (LIN_BK * LIN_WARPS)) == 0;
     for (int l = 0; l < c.mod_depth; ++l) {
         const ModW& mw = h->mod_layers[l];
@@ -1216,8 +1218,10 @@ int fsar_create(const fsar_config* cfg, fsar_handle** out) {
             cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.device);
             if (coop && (smem <= 48 * 1024 || cudaFuncSetAttribute(modulator_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                                    (int)smem) == cudaSuccess) &&
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, modulator_fused_kernel, LIN_THREADS, smem) == cudaSuccess)
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, modulator_fused_kernel, LIN_THREADS, smem) == cudaSuccess) {
                 h->mod_fused_ctas_per_sm = per_sm;
+                h->mod_fused_smem_max = smem;
+            }
             else
                 cudaGetLastError();
         }
