@@ -6,7 +6,6 @@ import subprocess
 import sys
 import types
 
-import numpy as np
 import pytest
 import torch
 

@@ -1,6 +1,6 @@
 """LayerNorm over the 96-frame residual stream (18912 x 768 fp32 -> fp16): L2-warm (same buffer back to back: 58 + 29 MB fit the
 126 MB L2) vs cold (eight buffers in rotation). Tells how much of the in-situ 17-18 us per launch is DRAM."""
-import json, os, sys, time
+import json, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
